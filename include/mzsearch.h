@@ -1,0 +1,173 @@
+/*
+ * mzsearch.h — C ABI of libmzsearch.so: the B200-native batched MuZero search that drops in behind
+ * muax.MuZero.act / muax.policy.Policy.
+ *
+ * The reference has no native interface on this path: `MuZero._plan` (muax/model.py:222-243) hands a
+ * `RootFnOutput` and the `_recurrent_inference` callback (muax/model.py:265-282) to
+ * `mctx.muzero_policy` / `mctx.gumbel_muzero_policy` (muax/policy.py:13-47) and XLA compiles the lot.
+ * These entry points are what an FFI for that call would bind; each one cites the reference
+ * interface it replaces.  Plain pointers and sizes only — no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every `*_dev` pointer is device memory on `mz_config.device`, caller-owned, borrowed for the
+ *     duration of the stream-ordered call; `stream` is a cudaStream_t passed as void* (NULL = default);
+ *   - a handle is NOT thread-safe; use one handle per (device, stream);
+ *   - every function returns 0 on success; on failure a message is available from mz_last_error();
+ *   - the library never falls back to a CPU path: without a usable CUDA device mz_create fails.
+ */
+#ifndef MZSEARCH_H_
+#define MZSEARCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZ_MAX_LAYERS 8
+#define MZ_MAX_ACTIONS 32
+
+#define MZ_POLICY_MUZERO 0 /* mctx.muzero_policy        — muax/policy.py:13-30 */
+#define MZ_POLICY_GUMBEL 1 /* mctx.gumbel_muzero_policy — muax/policy.py:33-47 */
+
+#define MZ_QTRANSFORM_BY_PARENT_AND_SIBLINGS 0 /* what MuZero.act forces: muax/model.py:230-231 */
+#define MZ_QTRANSFORM_COMPLETED_BY_MIX_VALUE 1 /* mctx's default for the Gumbel policy: muax/policy.py:44 */
+
+#define MZ_PRNG_THREEFRY_LEGACY 0        /* jax_threefry_partitionable = False (JAX < 0.5.0) */
+#define MZ_PRNG_THREEFRY_PARTITIONABLE 1 /* jax_threefry_partitionable = True */
+
+#define MZ_ACT_ELU 0  /* jax.nn.elu — muax/nn.py:78-104 */
+#define MZ_ACT_RELU 1
+
+#define MZ_ENGINE_AUTO 0
+#define MZ_ENGINE_STEPWISE 1 /* select / recurrent / backup kernels per simulation, trees in HBM */
+#define MZ_ENGINE_FUSED 2    /* one persistent launch per act, trees resident in shared memory */
+
+/* One hk.Sequential of hk.Linear layers with an activation between layers (none after the last):
+ * muax/nn.py:63-65, 77-84, 97-104.  Offsets are in floats into the weight blob; W is [in][out]
+ * row-major (haiku's layout, y = x @ W + b), b is [out]. */
+typedef struct mz_stack {
+  int32_t n_layers;
+  int32_t in_dim[MZ_MAX_LAYERS];
+  int32_t out_dim[MZ_MAX_LAYERS];
+  int64_t w_off[MZ_MAX_LAYERS];
+  int64_t b_off[MZ_MAX_LAYERS];
+} mz_stack;
+
+/* Static shape of one search engine instance: replaces the static arguments of the jitted
+ * `MuZero._plan` (muax/model.py:222) plus the network definitions of muax/nn.py:59-115. */
+typedef struct mz_config {
+  int32_t batch;               /* rows (environments / trees) owned by this handle */
+  int32_t num_actions;         /* A, 1..MZ_MAX_ACTIONS */
+  int32_t embed_dim;           /* E */
+  int32_t obs_dim;             /* flat observation size; 0 if roots are always supplied by the caller */
+  int32_t support_size;        /* S; value/reward heads have 2S+1 logits (muax/model.py:48,260) */
+  int32_t max_num_simulations; /* capacity: the tree workspace holds max_num_simulations + 1 nodes */
+  int32_t activation;          /* MZ_ACT_* */
+  int32_t repr_minmax;         /* min_max_normalize after Representation (muax/nn.py:69) */
+  int32_t dyn_minmax;          /* min_max_normalize on the next state (muax/nn.py:114) */
+  int32_t prng_mode;           /* MZ_PRNG_* */
+  int32_t device;              /* CUDA device ordinal */
+  float discount;              /* muax/model.py:47,275 */
+  mz_stack repr;               /* obs -> s                     (muax/nn.py:59-70)  */
+  mz_stack pred_v;             /* s -> value logits [2S+1]      (muax/nn.py:77-80)  */
+  mz_stack pred_pi;            /* s -> policy logits [A]        (muax/nn.py:81-84)  */
+  mz_stack dyn_ns;             /* [s, onehot(a)] -> next s      (muax/nn.py:97-100) */
+  mz_stack dyn_r;              /* [s, onehot(a)] -> reward logits (muax/nn.py:101-104) */
+} mz_config;
+
+/* Per-call arguments: the keyword arguments of MuZero.act / Policy.__call__
+ * (muax/model.py:82-96, muax/policy.py:17-30, 37-47). */
+typedef struct mz_search_args {
+  int32_t policy;         /* MZ_POLICY_* */
+  int32_t qtransform;     /* MZ_QTRANSFORM_* */
+  int32_t num_simulations;
+  int32_t max_depth;      /* <= 0 means None */
+  int32_t max_considered; /* max_num_considered_actions (Gumbel) */
+  int32_t global_batch;   /* rows of the whole (multi-GPU) batch; <= 0 means == batch */
+  int32_t batch_offset;   /* global index of this handle's row 0 (PRNG draws are indexed globally) */
+  int32_t engine;         /* MZ_ENGINE_* */
+  float temperature;
+  float dirichlet_fraction;
+  float dirichlet_alpha;
+  float pb_c_init;
+  float pb_c_base;
+  float gumbel_scale;
+  float value_scale;      /* qtransform_completed_by_mix_value, default 0.1 */
+  float maxvisit_init;    /* qtransform_completed_by_mix_value, default 50 */
+  uint32_t key0, key1;    /* the jax PRNGKey words */
+} mz_search_args;
+
+/* Device views of the search tree after a search (mctx.Tree field names).
+ * [B,N], [B,N,A] and [B,N,E] row-major; valid until the next call on the handle. */
+typedef struct mz_tree_view {
+  int32_t batch, num_nodes, num_actions, embed_dim;
+  const int32_t *node_visits, *parents, *action_from_parent, *children_index, *children_visits;
+  const float *raw_values, *node_values, *children_prior_logits, *children_values, *children_rewards,
+      *children_discounts, *embeddings;
+  const float* root_noise;   /* [B,A] dirichlet noise / root gumbel actually used */
+  const int32_t* sim_depth;  /* [B,num_simulations] selected path length per simulation */
+} mz_tree_view;
+
+typedef struct mz_handle mz_handle;
+
+const char* mz_last_error(void);
+
+/* Fills `args` with the reference defaults (muax/model.py:82-96, muax/policy.py:17-47). */
+void mz_default_args(mz_search_args* args);
+
+/* Replaces `MuZero.__init__` + the first (compiling) `_plan` call: allocates the tree workspace. */
+int mz_create(mz_handle** out, const mz_config* cfg);
+int mz_destroy(mz_handle* h);
+
+/* Replaces passing `params` into `_plan` (muax/model.py:162): copies the fp32 weight blob (layout given
+ * by the mz_stack offsets in mz_config).  `on_device` != 0: `blob` is device memory. */
+int mz_set_weights(mz_handle* h, const float* blob, size_t n_floats, int on_device, void* stream);
+
+/* Replaces `MuZero._plan` (muax/model.py:222-243): root inference + policy + search + action.
+ * Root: give `obs_dev` [B,obs_dim] (the library runs Representation + Prediction, model.py:251-263); or
+ * obs_dev == NULL and root_emb_dev [B,E] from the caller's own Representation (e.g. a conv torso) — the
+ * library then runs Prediction on it; or additionally root_logits_dev [B,A] + root_value_dev [B] = a
+ * complete RootFnOutput computed by the caller.
+ * invalid_dev: [B,A] uint8, 1 = invalid, or NULL.  noise_dev: [B,A] injected Dirichlet noise (MuZero) or
+ * root Gumbel (Gumbel policy), or NULL to draw on device.
+ * Outputs: action [B] int32, action_weights [B,A], root_value [B] (raw network value, model.py:243). */
+int mz_search(mz_handle* h, const float* obs_dev, const float* root_logits_dev, const float* root_value_dev,
+              const float* root_emb_dev, const uint8_t* invalid_dev, const float* noise_dev,
+              const mz_search_args* args, int32_t* action_out_dev, float* action_weights_out_dev,
+              float* root_value_out_dev, void* stream);
+
+/* Same call with HOST buffers (what `MuZero.act` sees: numpy in, numpy out — model.py:160-174): stages
+ * through pinned memory, copies H2D, searches, copies D2H and synchronises the stream. */
+int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_host, const float* noise_host,
+                   const mz_search_args* args, int32_t* action_out_host, float* action_weights_out_host,
+                   float* root_value_out_host, void* stream);
+
+/* Callback mode — for networks the declarative stacks cannot express.  The caller plays mctx's
+ * `recurrent_fn` (muax/model.py:265-282) between mz_select and mz_expand_backup:
+ *   mz_begin(root, ...); for sim in range(num_simulations): mz_select -> recurrent_fn -> mz_expand_backup;
+ *   mz_finish(...). */
+int mz_begin(mz_handle* h, const float* root_logits_dev, const float* root_value_dev, const float* root_emb_dev,
+             const uint8_t* invalid_dev, const float* noise_dev, const mz_search_args* args, void* stream);
+/* parent_emb_out_dev [B,E] = embeddings[b, parent[b]]; action_out_dev [B]. */
+int mz_select(mz_handle* h, int32_t sim, int32_t* action_out_dev, float* parent_emb_out_dev, void* stream);
+int mz_expand_backup(mz_handle* h, int32_t sim, const float* reward_dev, const float* discount_dev,
+                     const float* prior_logits_dev, const float* value_dev, const float* next_emb_dev, void* stream);
+int mz_finish(mz_handle* h, int32_t* action_out_dev, float* action_weights_out_dev, void* stream);
+
+int mz_get_tree(mz_handle* h, mz_tree_view* view);
+
+/* Number of kernels this library launched on behalf of the handle since creation. */
+int mz_launch_count(mz_handle* h, int64_t* count);
+/* Device time (ms, CUDA events on `stream`) of the search kernels of the last mz_search* call. */
+int mz_last_kernel_ms(mz_handle* h, float* ms);
+
+/* Evaluates include/mz_math.h device functions elementwise (bit-parity tests against the host build).
+ * kind: 0 expf, 1 logf, 2 expm1f, 3 inv_scaling, 4 gumbel-from-bits (x reinterpreted as uint32). */
+int mz_math_probe(int32_t kind, const float* x_dev, float* y_dev, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MZSEARCH_H_ */
