@@ -155,55 +155,9 @@ __global__ void __launch_bounds__(kTreeThreads) begin_kernel(Tree t, SearchParam
   if (b >= t.B) return;
   const int a = threadIdx.x & (G - 1);
   const unsigned m = group_mask<G>();
-  const int A = t.A;
-  const bool ok = a < A;
-  const long gb = (long)p.batch_offset + b;
-  float logit = ok ? root_logits[(long)b * A + a] : 0.0f;
-  const bool inv = ok && invalid != nullptr && invalid[(long)b * A + a] != 0;
-  float nz = 0.0f;
-  if (p.policy == MZ_POLICY_MUZERO) {
-    const float prob = group_softmax<G>(logit, ok, A, m);
-    if (noise != nullptr) {
-      nz = ok ? noise[(long)b * A + a] : 0.0f;
-    } else {
-      const float g = ok ? gamma_draw(p.aux_key0, p.aux_key1, (uint32_t)(gb * A + a), p.dirichlet_alpha) : 0.0f;
-      const float s = gsum_seq<G>(g, A, m);
-      nz = s > 0.0f ? MZ_DIV(g, s) : MZ_DIV(1.0f, (float)A);
-    }
-    const float noisy = MZ_ADD(MZ_MUL(MZ_SUB(1.0f, p.dirichlet_fraction), prob), MZ_MUL(p.dirichlet_fraction, nz));
-    logit = mz_logf(fmaxf(noisy, MZ_F32_TINY));
-    if (invalid != nullptr) {
-      const float mx = gmax<G>(ok ? logit : -mz_inf(), m);
-      logit = inv ? -MZ_F32_MAX : MZ_SUB(logit, mx);
-    }
-  } else {
-    if (invalid != nullptr) {
-      const float mx = gmax<G>(ok ? logit : -mz_inf(), m);
-      logit = inv ? -MZ_F32_MAX : MZ_SUB(logit, mx);
-    }
-    if (noise != nullptr) {
-      nz = ok ? noise[(long)b * A + a] : 0.0f;
-    } else if (ok) {
-      const uint32_t bits =
-          bits_word(p.aux_key0, p.aux_key1, (uint32_t)p.global_batch * (uint32_t)A, (uint32_t)(gb * A + a), p.prng_mode);
-      nz = MZ_MUL(p.gumbel_scale, mz_bits_to_gumbel(bits));
-    }
-  }
-  const float prob = group_softmax<G>(logit, ok, A, m);
-  const long tb = (long)b * t.N;
-  if (ok) {
-    t.children_prior_logits[tb * A + a] = logit;
-    t.children_prior_probs[tb * A + a] = prob;
-    t.root_noise[(long)b * A + a] = nz;
-    t.root_invalid[(long)b * A + a] = inv ? 1 : 0;
-  }
-  for (int e = a; e < t.E; e += G) t.embeddings[tb * t.E + e] = root_emb[(long)b * t.E + e];
-  if (a == 0) {
-    const float v = root_value[b];
-    t.raw_values[tb] = v;
-    t.node_values[tb] = v;
-    t.node_visits[tb] = 1;
-  }
+  const long ba = (long)b * t.A;
+  group_begin<G>(t, p, b, (long)p.batch_offset + b, root_logits + ba, root_value[b], root_emb + (long)b * t.E,
+                 invalid != nullptr ? invalid + ba : nullptr, noise != nullptr ? noise + ba : nullptr, a, m);
 }
 
 struct SelectIO {
@@ -304,39 +258,10 @@ __global__ void __launch_bounds__(kTreeThreads) finish_kernel(Tree t, SearchPara
   if (b >= t.B) return;
   const int a = threadIdx.x & (G - 1);
   const unsigned m = group_mask<G>();
-  const int A = t.A;
-  const bool ok = a < A;
-  const long tb = (long)b * t.N;
-  const long gb = (long)p.batch_offset + b;
-  const ChildRow c = load_child(t, tb * A + (ok ? a : 0), ok);
-  float score, weight;
-  if (p.policy == MZ_POLICY_MUZERO) {
-    const float vc = (float)c.visits;
-    const float total = gsum_seq<G>(ok ? vc : 0.0f, A, m);
-    weight = total > 0.0f ? MZ_DIV(vc, fmaxf(total, 1.0f)) : MZ_DIV(1.0f, (float)A);
-    float l = mz_logf(fmaxf(weight, MZ_F32_TINY));
-    const float mx = gmax<G>(ok ? l : -mz_inf(), m);
-    l = MZ_DIV(MZ_SUB(l, mx), fmaxf(MZ_F32_TINY, p.temperature));
-    const uint32_t bits = bits_word(p.final_key0, p.final_key1, (uint32_t)p.global_batch * (uint32_t)A,
-                                    (uint32_t)(gb * A + (ok ? a : 0)), p.prng_mode);
-    score = ok ? MZ_ADD(mz_bits_to_gumbel(bits), l) : -mz_inf();
-  } else {
-    const bool inv = ok && t.root_invalid[(long)b * A + a] != 0;
-    const int cv = gmax_i<G>(ok ? c.visits : 0, m);
-    const float q = group_qtransform<G>(p.qtransform, c, ok, A, t.node_values[tb], t.raw_values[tb], p.value_scale,
-                                        p.maxvisit_init, m);
-    const float gumbel = ok ? t.root_noise[(long)b * A + a] : 0.0f;
-    score = group_score_considered<G>(cv, gumbel, c.logit, q, c.visits, ok, m);
-    if (inv) score = -mz_inf();
-    float x = MZ_ADD(c.logit, q);
-    if (has_invalid) {
-      const float mx = gmax<G>(ok ? x : -mz_inf(), m);
-      x = inv ? -MZ_F32_MAX : MZ_SUB(x, mx);
-    }
-    weight = group_softmax<G>(x, ok, A, m);
-  }
-  const int action = gargmax_first<G>(score, a, m);
-  if (ok) weights_out[(long)b * A + a] = weight;
+  int action;
+  float weight;
+  group_finish<G>(t, p, b, (long)p.batch_offset + b, has_invalid, a, m, action, weight);
+  if (a < t.A) weights_out[(long)b * t.A + a] = weight;
   if (a == 0) action_out[b] = action;
 }
 
@@ -618,6 +543,7 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   if (engine == MZ_ENGINE_FUSED) {
     if (!fused_ok) return fail("the fused engine does not support this configuration (see DESIGN.md)");
     h->has_invalid = invalid != nullptr;
+    if (args->num_simulations + 1 < h->N && clear_tree(h, args->num_simulations, true, stream)) return 1;
     std::string err;
     if (fused_launch(h->fused, h->net, h->weights, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
                      root_value_out, stream, &err))
