@@ -17,6 +17,7 @@
 
 #include "mz_device.cuh"
 #include "mz_fused.cuh"
+#include "mz_group.cuh"
 
 namespace mz {
 
@@ -318,6 +319,7 @@ struct mz_handle {
   bool timed = false;
   std::vector<void*> allocs;
   mz::FusedState fused;
+  mz::GroupState group;
 };
 
 namespace mz {
@@ -538,17 +540,26 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   if (stage_keys(h, args, stream)) return 1;
   MZ_CUDA(cudaEventRecord(h->ev_start, stream));
   int engine = args->engine;
-  const bool fused_ok = obs != nullptr && fused_supported(h->fused, h->net, h->params);
-  if (engine == MZ_ENGINE_AUTO) engine = fused_ok ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE;
-  if (engine == MZ_ENGINE_FUSED) {
-    if (!fused_ok) return fail("the fused engine does not support this configuration (see DESIGN.md)");
+  const bool group_ok = obs != nullptr && h->weights != nullptr && group_supported(h->group, h->params, h->cfg.batch);
+  const bool fused_ok = obs != nullptr && h->weights != nullptr && fused_supported(h->fused, h->net, h->params);
+  if (engine == MZ_ENGINE_AUTO) engine = (group_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE;
+  if (engine == MZ_ENGINE_FUSED && !group_ok) engine = MZ_ENGINE_FUSED_CTA;
+  if (engine == MZ_ENGINE_FUSED || engine == MZ_ENGINE_FUSED_CTA) {
+    if (engine == MZ_ENGINE_FUSED_CTA && !fused_ok)
+      return fail("the fused engine does not support this configuration (see DESIGN.md)");
     h->has_invalid = invalid != nullptr;
     if (args->num_simulations + 1 < h->N && clear_tree(h, args->num_simulations, true, stream)) return 1;
     std::string err;
-    if (fused_launch(h->fused, h->net, h->weights, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
-                     root_value_out, stream, &err))
-      return fail(err);
-    h->launches += 1;
+    if (engine == MZ_ENGINE_FUSED) {
+      if (group_launch(h->group, h->tree, h->params, obs, invalid, noise, action_out, weights_out, root_value_out,
+                       stream, &h->launches, &err))
+        return fail(err);
+    } else {
+      if (fused_launch(h->fused, h->net, h->weights, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
+                       root_value_out, stream, &err))
+        return fail(err);
+      h->launches += 1;
+    }
   } else {
     if (obs != nullptr || root_logits == nullptr) {  // Prediction (and Representation) run in the library
       if (launch_root(h, obs, obs != nullptr ? nullptr : root_emb, stream)) return 1;
@@ -720,7 +731,8 @@ int mz_create(mz_handle** out, const mz_config* cfg) {
   MZ_TRY(cudaEventCreate(&h->ev_stop) != cudaSuccess ? fail("cudaEventCreate failed") : 0);
   {
     std::string err;
-    if (fused_init(h->fused, h->net, cfg->batch, cfg->max_num_simulations, cfg->device, &err)) {
+    if (fused_init(h->fused, h->net, cfg->batch, cfg->max_num_simulations, cfg->device, &err) ||
+        group_init(h->group, h->net, cfg->device, &err)) {
       mz_destroy(h);
       return fail(err);
     }
@@ -735,6 +747,7 @@ int mz_destroy(mz_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   mz::fused_destroy(h->fused);
+  mz::group_destroy(h->group);
   for (void* p : h->allocs) cudaFree(p);
   if (h->weights) cudaFree(h->weights);
   if (h->table_dev) cudaFree(h->table_dev);
@@ -759,6 +772,7 @@ int mz_set_weights(mz_handle* h, const float* blob, size_t n_floats, int on_devi
   if (h->weights == nullptr) MZ_CUDA(cudaMalloc((void**)&h->weights, std::max(h->n_weights, (size_t)4) * sizeof(float) + 16));
   MZ_CUDA(cudaMemcpyAsync(h->weights, blob, h->n_weights * sizeof(float),
                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  if (group_pack(h->group, h->weights, s, &h->launches)) return fail("packing the weights for the group engine failed");
   if (!on_device) MZ_CUDA(cudaStreamSynchronize(s));  // the host blob may be pageable and short-lived
   return 0;
 }

@@ -47,14 +47,14 @@ def _collect(eng, action, weights, root_value):
     return got
 
 
-ENGINES = [1, 2]  # MZ_ENGINE_STEPWISE, MZ_ENGINE_FUSED
+ENGINES = [1, 2, 3]  # MZ_ENGINE_STEPWISE, MZ_ENGINE_FUSED (group kernel when it fits), MZ_ENGINE_FUSED_CTA
 
 
 def _fused_or_skip(eng, engine_id, run):
     try:
         return run()
     except RuntimeError as e:
-        if engine_id == 2 and "fused engine" in str(e):
+        if engine_id in (2, 3) and "fused engine" in str(e):
             pytest.skip("fused engine does not cover this configuration")
         raise
 
