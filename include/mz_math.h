@@ -92,13 +92,56 @@ MZ_HD float mz_exp_poly(float r) {
   return p;
 }
 
+/* exp(x).  Written branch-free (selects only) so that a warp evaluating it on mixed arguments does not
+ * serialise; the value for every input is the same as the textbook early-return formulation it replaced
+ * (checked over all 2^32 inputs by tests/test_mz_math.py::test_branch_free_forms_are_exhaustively_identical). */
 MZ_HD float mz_expf(float x) {
+  const float xc = mz_fmin(mz_fmax(x, -104.0f), 89.0f); /* keeps n inside [-151, 129]; NaN handled below */
+  const float nf = MZ_RINT(MZ_MUL(xc, 1.44269504088896341f));
+  float r = MZ_FMA(nf, -0.693359375f, xc);   /* ln2 high part: 8 significant bits, nf*hi is exact */
+  r = MZ_FMA(nf, 2.12194440e-4f, r);         /* minus the (negative) low part */
+  const float p = mz_exp_poly(r);
+  const float y = MZ_ADD(MZ_FMA(p, MZ_MUL(r, r), r), 1.0f);
+  const int n = (int)nf;
+  const int n1 = n / 2;
+  const int n2 = n - n1;
+  float v = MZ_MUL(MZ_MUL(y, mz_pow2i(n1)), mz_pow2i(n2));
+  v = x > 88.72283905f ? mz_inf() : v;
+  v = x < -103.972084f ? 0.0f : v;
+  return x != x ? x : v;
+}
+
+/* expm1 for the ELU branch (x <= 0 in practice); accurate relative to x near 0.  Branch-free: for
+ * |x| < ln2/2 the range reduction of mz_expf gives n = 0 and r = x, so both branches share r, p and
+ * z = p*r^2 + r; the small branch returns z, the other one (z + 1) * 2^n - 1. */
+MZ_HD float mz_expm1f(float x) {
+  const float xc = mz_fmin(mz_fmax(x, -104.0f), 89.0f);
+  const float nf = MZ_RINT(MZ_MUL(xc, 1.44269504088896341f));
+  float r = MZ_FMA(nf, -0.693359375f, xc);
+  r = MZ_FMA(nf, 2.12194440e-4f, r);
+  const float p = mz_exp_poly(r);
+  const float z = MZ_FMA(p, MZ_MUL(r, r), r);
+  const int n = (int)nf;
+  const int n1 = n / 2;
+  const int n2 = n - n1;
+  float e = MZ_MUL(MZ_MUL(MZ_ADD(z, 1.0f), mz_pow2i(n1)), mz_pow2i(n2));
+  e = x > 88.72283905f ? mz_inf() : e;
+  e = x < -103.972084f ? 0.0f : e;
+  const float big = MZ_SUB(e, 1.0f);
+  const float v = mz_fabs(x) < 0.34657359f ? z : big;
+  return x != x ? x : v;
+}
+
+/* Early-return reference formulations (what the branch-free mz_expf / mz_expm1f must equal bit for bit);
+ * compiled only into the CPU checker for the exhaustive equivalence test. */
+#if !defined(__CUDACC__)
+static inline float mz_expf_ref(float x) {
   if (x != x) return x;
   if (x > 88.72283905f) return mz_inf();
   if (x < -103.972084f) return 0.0f;
   float nf = MZ_RINT(MZ_MUL(x, 1.44269504088896341f));
-  float r = MZ_FMA(nf, -0.693359375f, x);    /* ln2 high part: 8 significant bits, nf*hi is exact */
-  r = MZ_FMA(nf, 2.12194440e-4f, r);         /* minus the (negative) low part */
+  float r = MZ_FMA(nf, -0.693359375f, x);
+  r = MZ_FMA(nf, 2.12194440e-4f, r);
   float p = mz_exp_poly(r);
   float y = MZ_ADD(MZ_FMA(p, MZ_MUL(r, r), r), 1.0f);
   int n = (int)nf;
@@ -106,15 +149,14 @@ MZ_HD float mz_expf(float x) {
   int n2 = n - n1;
   return MZ_MUL(MZ_MUL(y, mz_pow2i(n1)), mz_pow2i(n2));
 }
-
-/* expm1 for the ELU branch (x <= 0 in practice); accurate relative to x near 0. */
-MZ_HD float mz_expm1f(float x) {
+static inline float mz_expm1f_ref(float x) {
   if (mz_fabs(x) < 0.34657359f) {
     float p = mz_exp_poly(x);
     return MZ_FMA(p, MZ_MUL(x, x), x);
   }
-  return MZ_SUB(mz_expf(x), 1.0f);
+  return MZ_SUB(mz_expf_ref(x), 1.0f);
 }
+#endif
 
 MZ_HD float mz_logf(float x) {
   if (x != x) return x;

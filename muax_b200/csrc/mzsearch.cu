@@ -18,6 +18,7 @@
 #include "mz_device.cuh"
 #include "mz_fused.cuh"
 #include "mz_group.cuh"
+#include "mz_lane.cuh"
 
 namespace mz {
 
@@ -320,6 +321,7 @@ struct mz_handle {
   std::vector<void*> allocs;
   mz::FusedState fused;
   mz::GroupState group;
+  mz::LaneState lanes;
 };
 
 namespace mz {
@@ -540,17 +542,24 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   if (stage_keys(h, args, stream)) return 1;
   MZ_CUDA(cudaEventRecord(h->ev_start, stream));
   int engine = args->engine;
-  const bool group_ok = obs != nullptr && h->weights != nullptr && group_supported(h->group, h->params, h->cfg.batch);
-  const bool fused_ok = obs != nullptr && h->weights != nullptr && fused_supported(h->fused, h->net, h->params);
-  if (engine == MZ_ENGINE_AUTO) engine = (group_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE;
-  if (engine == MZ_ENGINE_FUSED && !group_ok) engine = MZ_ENGINE_FUSED_CTA;
-  if (engine == MZ_ENGINE_FUSED || engine == MZ_ENGINE_FUSED_CTA) {
-    if (engine == MZ_ENGINE_FUSED_CTA && !fused_ok)
+  const bool have_w = obs != nullptr && h->weights != nullptr;
+  const bool lane_ok = have_w && lane_supported(h->lanes, h->params);
+  const bool group_ok = have_w && group_supported(h->group, h->params, h->cfg.batch);
+  const bool fused_ok = have_w && fused_supported(h->fused, h->net, h->params);
+  enum { kLane = 100 };
+  if (engine == MZ_ENGINE_AUTO) engine = (lane_ok || group_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE;
+  if (engine == MZ_ENGINE_FUSED) engine = lane_ok ? (int)kLane : (group_ok ? MZ_ENGINE_FUSED_GROUP : MZ_ENGINE_FUSED_CTA);
+  if (engine == kLane || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
+    if ((engine == MZ_ENGINE_FUSED_CTA && !fused_ok) || (engine == MZ_ENGINE_FUSED_GROUP && !group_ok))
       return fail("the fused engine does not support this configuration (see DESIGN.md)");
     h->has_invalid = invalid != nullptr;
     if (args->num_simulations + 1 < h->N && clear_tree(h, args->num_simulations, true, stream)) return 1;
     std::string err;
-    if (engine == MZ_ENGINE_FUSED) {
+    if (engine == kLane) {
+      if (lane_launch(h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out, root_value_out,
+                      stream, &h->launches, &err))
+        return fail(err);
+    } else if (engine == MZ_ENGINE_FUSED_GROUP) {
       if (group_launch(h->group, h->tree, h->params, obs, invalid, noise, action_out, weights_out, root_value_out,
                        stream, &h->launches, &err))
         return fail(err);
@@ -732,7 +741,7 @@ int mz_create(mz_handle** out, const mz_config* cfg) {
   {
     std::string err;
     if (fused_init(h->fused, h->net, cfg->batch, cfg->max_num_simulations, cfg->device, &err) ||
-        group_init(h->group, h->net, cfg->device, &err)) {
+        group_init(h->group, h->net, cfg->device, &err) || lane_init(h->lanes, h->net, cfg->device, &err)) {
       mz_destroy(h);
       return fail(err);
     }
@@ -748,6 +757,7 @@ int mz_destroy(mz_handle* h) {
   cudaDeviceSynchronize();
   mz::fused_destroy(h->fused);
   mz::group_destroy(h->group);
+  mz::lane_destroy(h->lanes);
   for (void* p : h->allocs) cudaFree(p);
   if (h->weights) cudaFree(h->weights);
   if (h->table_dev) cudaFree(h->table_dev);
@@ -772,7 +782,8 @@ int mz_set_weights(mz_handle* h, const float* blob, size_t n_floats, int on_devi
   if (h->weights == nullptr) MZ_CUDA(cudaMalloc((void**)&h->weights, std::max(h->n_weights, (size_t)4) * sizeof(float) + 16));
   MZ_CUDA(cudaMemcpyAsync(h->weights, blob, h->n_weights * sizeof(float),
                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-  if (group_pack(h->group, h->weights, s, &h->launches)) return fail("packing the weights for the group engine failed");
+  if (group_pack(h->group, h->weights, s, &h->launches) || lane_pack(h->lanes, h->weights, s, &h->launches))
+    return fail("re-packing the weights for the fused engines failed");
   if (!on_device) MZ_CUDA(cudaStreamSynchronize(s));  // the host blob may be pageable and short-lived
   return 0;
 }

@@ -253,3 +253,12 @@ def pb_c(visits, pb_c_init=1.25, pb_c_base=19652.0):
     lib().mzo_pb_c(_ptr(visits, ctypes.c_int32), ctypes.c_int(visits.shape[0]), ctypes.c_float(pb_c_init),
                    ctypes.c_float(pb_c_base), _ptr(out, ctypes.c_float))
     return out
+
+
+def check_branch_free(lo, hi):
+    """Counts inputs in the uint32 bit-pattern range [lo, hi] where the branch-free mz_expf/mz_expm1f differ
+    from the early-return reference forms."""
+    lib().mzo_check_branch_free.restype = ctypes.c_int64
+    first = ctypes.c_uint32(0)
+    n = lib().mzo_check_branch_free(ctypes.c_uint32(lo), ctypes.c_uint32(hi), ctypes.byref(first))
+    return int(n), int(first.value)

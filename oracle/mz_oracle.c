@@ -776,3 +776,20 @@ void mzo_min_max_normalize(float *s, int rows, int n) {
 void mzo_pb_c(const int32_t *visits, int n, float pb_c_init, float pb_c_base, float *out) {
   for (int i = 0; i < n; ++i) out[i] = pb_c_of((float)visits[i], pb_c_init, pb_c_base);
 }
+
+/* Exhaustive check over all 2^32 float bit patterns: branch-free mz_expf / mz_expm1f == early-return forms.
+ * Returns the number of mismatching inputs (NaN results compare equal when both are NaN). */
+static int same_bits(float a, float b) { return (a != a && b != b) || mz_f2u(a) == mz_f2u(b); }
+int64_t mzo_check_branch_free(uint32_t lo, uint32_t hi_inclusive, uint32_t *first_bad) {
+  int64_t bad = 0;
+  uint64_t u = lo;
+  for (;; ++u) {
+    float x = mz_u2f((uint32_t)u);
+    if (!same_bits(mz_expf(x), mz_expf_ref(x)) || !same_bits(mz_expm1f(x), mz_expm1f_ref(x))) {
+      if (bad == 0 && first_bad) *first_bad = (uint32_t)u;
+      ++bad;
+    }
+    if (u == hi_inclusive) break;
+  }
+  return bad;
+}

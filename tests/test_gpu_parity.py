@@ -47,14 +47,14 @@ def _collect(eng, action, weights, root_value):
     return got
 
 
-ENGINES = [1, 2, 3]  # MZ_ENGINE_STEPWISE, MZ_ENGINE_FUSED (group kernel when it fits), MZ_ENGINE_FUSED_CTA
+ENGINES = [1, 2, 3, 4]  # MZ_ENGINE_STEPWISE, MZ_ENGINE_FUSED (best fused: lane engine), _FUSED_CTA, _FUSED_GROUP
 
 
 def _fused_or_skip(eng, engine_id, run):
     try:
         return run()
     except RuntimeError as e:
-        if engine_id in (2, 3) and "fused engine" in str(e):
+        if engine_id != 1 and "fused engine" in str(e):
             pytest.skip("fused engine does not cover this configuration")
         raise
 

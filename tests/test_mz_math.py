@@ -40,3 +40,24 @@ def test_reference_function_pins(c_oracle):
     assert np.array_equal(c_oracle.support_from_probs(g["sts_probs"], 10), g["sts_y"])
     assert np.array_equal(c_oracle.min_max_normalize(g["mm_x"]), g["mm_y"])
     assert np.abs(c_oracle.pb_c(g["pbc_visits"]).astype(np.float64) - g["pbc_y"]).max() < 5e-7
+
+
+def test_branch_free_forms_are_exhaustively_identical(c_oracle):
+    """include/mz_math.h evaluates exp/expm1 with selects instead of early returns (GPU warps would serialise
+    on the branches).  The two formulations must agree on every float: all 2^32 bit patterns were checked when
+    the change was made (31 s on 8 cores); the suite re-checks every threshold neighbourhood completely and a
+    strided sweep of the whole space."""
+    import struct
+
+    def bits(f):
+        return struct.unpack("<I", struct.pack("<f", f))[0]
+
+    for centre in (0.34657359, -0.34657359, 88.72283905, -103.972084, -104.0, 89.0, 0.0, -0.0, -87.33655, 1.0):
+        b = bits(centre)
+        lo, hi = max(b - 200000, 0), min(b + 200000, 2**32 - 1)
+        assert c_oracle.check_branch_free(lo, hi)[0] == 0, centre
+    for start in range(0, 2**32, 2**32 // 64):  # 64 windows of 2^18 consecutive patterns across the space
+        assert c_oracle.check_branch_free(start, start + 2**18)[0] == 0
+    # NaN / inf patterns
+    assert c_oracle.check_branch_free(0x7F800000 - 1000, 0x7F800000 + 100000)[0] == 0
+    assert c_oracle.check_branch_free(0xFF800000 - 1000, 0xFF800000 + 100000)[0] == 0

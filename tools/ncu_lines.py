@@ -44,9 +44,14 @@ def main():
             lines_by_off[int(m.group(1), 16)] = (cur_line, m.group(2))
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    # one section per profiled kernel: a "Kernel Name" row, a header row starting with "Address", then the body
+    want = sys.argv[4] if len(sys.argv) > 4 else kname.split("ILi")[0].split("kernel")[0]
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sec = next((i for i in starts if want in rows[i][1]), starts[0])
+    end = next((i for i in starts if i > sec), len(rows))
+    hdr_i = next(i for i in range(sec, end) if rows[i] and rows[i][0] == "Address")
     hdr = rows[hdr_i]
-    body = [dict(zip(hdr, r)) for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    body = [dict(zip(hdr, r)) for r in rows[hdr_i + 1:end] if len(r) == len(hdr)]
     base = int(body[0]["Address"], 16)
     agg, tot_i, tot_s = {}, 0.0, 0.0
     stall_cols = [c for c in hdr if c.startswith("stall_") and "Not Issued" not in c]
