@@ -186,24 +186,24 @@ def run_ours(args, wl, name):
                        support_size=wl["S"], max_num_simulations=NS, repr_minmax=wl["minmax"],
                        dyn_minmax=wl["minmax"], discount=0.99, device=dev)
     eng.set_weights(blob)
-    engine_id = {"auto": _lib.ENGINE_AUTO, "stepwise": _lib.ENGINE_STEPWISE, "fused": _lib.ENGINE_FUSED}[args.engine]
+    engine_id = {"auto": _lib.ENGINE_AUTO, "stepwise": _lib.ENGINE_STEPWISE, "fused": _lib.ENGINE_FUSED,
+                 "fused_cta": _lib.ENGINE_FUSED_CTA, "fused_group": _lib.ENGINE_FUSED_GROUP,
+                 "fused_lane": _lib.ENGINE_FUSED_LANE}[args.engine]
     obs_all = np.random.default_rng(1).standard_normal((GB, wl["obs_dim"])).astype(np.float32)
     obs_host = np.ascontiguousarray(obs_all[rank * B:(rank + 1) * B])
     obs_dev = torch.from_numpy(obs_host).to(dev)
     kw = dict(policy=wl["policy"], qtransform=wl["qtransform"], num_simulations=NS, global_batch=GB,
               batch_offset=rank * B, engine=engine_id)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-    gathered = None
-    if world > 1:
-        gathered = torch.empty(world, B, A + 2, dtype=torch.float32, device=dev)
+    from muax_b200.sharded import ShardedSearch
+    kw_local = {k: v for k, v in kw.items() if k not in ("global_batch", "batch_offset")}
+    sharded = ShardedSearch(lambda key, obs, **k2: eng.search(key, obs=obs, **k2), GB, A)
 
     def step_device(i):
+        # rows [rank*B, (rank+1)*B) of the global batch; with world > 1 this ends with the one all-gather of
+        # (action_weights, root_value, action) for the shared replay buffer (NCCL over NVLink)
         key = np.array([0, i], np.uint32)
-        a, w, v = eng.search(key, obs=obs_dev, **kw)
-        if world > 1:  # policies for the shared replay buffer: one all-gather per act over NVLink
-            packed = torch.cat([w, v[:, None], a[:, None].to(torch.float32)], dim=1)
-            dist.all_gather_into_tensor(gathered.view(world * B, A + 2), packed)
-        return a, w, v
+        return sharded.act(key, obs_dev, **kw_local)
 
     def step_host(i):
         key = np.array([0, i], np.uint32)
@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "stepwise", "fused"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "stepwise", "fused", "fused_cta", "fused_group", "fused_lane"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

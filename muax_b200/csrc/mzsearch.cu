@@ -548,9 +548,12 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   const bool fused_ok = have_w && fused_supported(h->fused, h->net, h->params);
   enum { kLane = 100 };
   if (engine == MZ_ENGINE_AUTO) engine = (lane_ok || group_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE;
-  if (engine == MZ_ENGINE_FUSED) engine = lane_ok ? (int)kLane : (group_ok ? MZ_ENGINE_FUSED_GROUP : MZ_ENGINE_FUSED_CTA);
+  // best fused variant first: measured on B200 (profiles/): group 0.78 ms, lane 0.99 ms, CTA-phased 1.5 ms per act
+  if (engine == MZ_ENGINE_FUSED) engine = group_ok ? MZ_ENGINE_FUSED_GROUP : (lane_ok ? (int)kLane : MZ_ENGINE_FUSED_CTA);
+  if (engine == MZ_ENGINE_FUSED_LANE) engine = kLane;
   if (engine == kLane || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
-    if ((engine == MZ_ENGINE_FUSED_CTA && !fused_ok) || (engine == MZ_ENGINE_FUSED_GROUP && !group_ok))
+    if ((engine == MZ_ENGINE_FUSED_CTA && !fused_ok) || (engine == MZ_ENGINE_FUSED_GROUP && !group_ok) ||
+        (engine == kLane && !lane_ok))
       return fail("the fused engine does not support this configuration (see DESIGN.md)");
     h->has_invalid = invalid != nullptr;
     if (args->num_simulations + 1 < h->N && clear_tree(h, args->num_simulations, true, stream)) return 1;

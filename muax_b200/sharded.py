@@ -1,0 +1,73 @@
+"""Env-batch sharding across GPUs (one process per GPU, torch.distributed).
+
+Trees are independent, so the search needs no collective: rank r owns global rows
+[offset_r, offset_r + count_r) and runs them with `global_batch` / `batch_offset` set, which makes every PRNG
+draw (per-tree simulate keys, root Dirichlet / Gumbel, final categorical) identical to the single-process run
+for ANY world size (legacy threefry `split(key, B)[b]` mixes b with B — SURVEY.md §8e).  The only exchange on
+the path is one all-gather per act of (action_weights, root_value, action) so that every rank can feed the
+shared replay buffer (the reference's `TrajectoryReplayBuffer`, muax/replay_buffer.py:154).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch: int, world_size: int, rank: int):
+    """Contiguous, as-even-as-possible row ranges: the first `global_batch % world_size` ranks get one extra."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    base, extra = divmod(int(global_batch), int(world_size))
+    count = base + (1 if rank < extra else 0)
+    offset = rank * base + min(rank, extra)
+    return offset, count
+
+
+def pack_outputs(action, weights, value):
+    """[n] i32, [n, A] f32, [n] f32 -> one [n, A + 2] f32 tensor (actions < 2^24 are exact in float32)."""
+    return torch.cat([weights, value[:, None], action[:, None].to(torch.float32)], dim=1)
+
+
+def unpack_outputs(packed):
+    A = packed.shape[1] - 2
+    return packed[:, A + 1].to(torch.int32), packed[:, :A].contiguous(), packed[:, A].contiguous()
+
+
+class ShardedSearch:
+    """Runs `search_fn` on this rank's rows and all-gathers the per-row outputs in global row order.
+
+    search_fn(rng_key, obs_local, global_batch=..., batch_offset=..., **kw) -> (action, weights, value) tensors;
+    with a `SearchEngine` pass `engine.search` (observations via `obs=`)."""
+
+    def __init__(self, search_fn, global_batch, num_actions, group=None):
+        self.search_fn = search_fn
+        self.global_batch = int(global_batch)
+        self.A = int(num_actions)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.offset, self.count = shard_bounds(self.global_batch, self.world, self.rank)
+        self.max_count = shard_bounds(self.global_batch, self.world, 0)[1]
+        self._gather_buf = None
+
+    def local_rows(self, global_tensor):
+        return global_tensor[self.offset:self.offset + self.count]
+
+    def act(self, rng_key, obs_local, **kw):
+        if obs_local.shape[0] != self.count:
+            raise ValueError(f"rank {self.rank} owns {self.count} rows, got {obs_local.shape[0]}")
+        action, weights, value = self.search_fn(rng_key, obs_local, global_batch=self.global_batch,
+                                                batch_offset=self.offset, **kw)
+        if self.world == 1:
+            return action, weights, value
+        packed = pack_outputs(action, weights, value)
+        if self.count < self.max_count:  # ragged shards: pad to the largest one for the fixed-size collective
+            pad = torch.zeros(self.max_count - self.count, self.A + 2, dtype=packed.dtype, device=packed.device)
+            packed = torch.cat([packed, pad], dim=0)
+        if (self._gather_buf is None or self._gather_buf.device != packed.device):
+            self._gather_buf = torch.empty(self.world * self.max_count, self.A + 2, dtype=torch.float32,
+                                           device=packed.device)
+        dist.all_gather_into_tensor(self._gather_buf, packed.contiguous(), group=self.group)
+        parts = []
+        for r in range(self.world):
+            _, cnt = shard_bounds(self.global_batch, self.world, r)
+            parts.append(self._gather_buf[r * self.max_count:r * self.max_count + cnt])
+        return unpack_outputs(torch.cat(parts, dim=0))
