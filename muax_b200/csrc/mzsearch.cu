@@ -19,6 +19,7 @@
 #include "mz_fused.cuh"
 #include "mz_group.cuh"
 #include "mz_lane.cuh"
+#include "mz_lane2.cuh"
 
 namespace mz {
 
@@ -322,6 +323,7 @@ struct mz_handle {
   mz::FusedState fused;
   mz::GroupState group;
   mz::LaneState lanes;
+  mz::Lane2State lane2;
 };
 
 namespace mz {
@@ -546,19 +548,26 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   const bool lane_ok = have_w && lane_supported(h->lanes, h->params);
   const bool group_ok = have_w && group_supported(h->group, h->params, h->cfg.batch);
   const bool fused_ok = have_w && fused_supported(h->fused, h->net, h->params);
-  enum { kLane = 100 };
+  const bool lane2_ok = lane_ok && lane2_supported(h->lane2, h->lanes, h->params);
+  enum { kLane = 100, kLane2 = 101 };
   if (engine == MZ_ENGINE_AUTO) engine = (lane_ok || group_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE;
   // best fused variant first: measured on B200 (profiles/): group 0.78 ms, lane 0.99 ms, CTA-phased 1.5 ms per act
-  if (engine == MZ_ENGINE_FUSED) engine = group_ok ? MZ_ENGINE_FUSED_GROUP : (lane_ok ? (int)kLane : MZ_ENGINE_FUSED_CTA);
+  if (engine == MZ_ENGINE_FUSED)
+    engine = lane2_ok ? (int)kLane2 : (group_ok ? MZ_ENGINE_FUSED_GROUP : (lane_ok ? (int)kLane : MZ_ENGINE_FUSED_CTA));
   if (engine == MZ_ENGINE_FUSED_LANE) engine = kLane;
-  if (engine == kLane || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
+  if (engine == MZ_ENGINE_FUSED_LANE2) engine = kLane2;
+  if (engine == kLane || engine == kLane2 || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
     if ((engine == MZ_ENGINE_FUSED_CTA && !fused_ok) || (engine == MZ_ENGINE_FUSED_GROUP && !group_ok) ||
-        (engine == kLane && !lane_ok))
+        (engine == kLane && !lane_ok) || (engine == kLane2 && !lane2_ok))
       return fail("the fused engine does not support this configuration (see DESIGN.md)");
     h->has_invalid = invalid != nullptr;
     if (args->num_simulations + 1 < h->N && clear_tree(h, args->num_simulations, true, stream)) return 1;
     std::string err;
-    if (engine == kLane) {
+    if (engine == kLane2) {
+      if (lane2_launch(h->lane2, h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
+                       root_value_out, stream, &h->launches, &err))
+        return fail(err);
+    } else if (engine == kLane) {
       if (lane_launch(h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out, root_value_out,
                       stream, &h->launches, &err))
         return fail(err);
@@ -748,6 +757,7 @@ int mz_create(mz_handle** out, const mz_config* cfg) {
       mz_destroy(h);
       return fail(err);
     }
+    lane2_init(h->lane2, h->lanes, h->net, h->lanes.max_smem);
   }
 #undef MZ_TRY
   *out = h;

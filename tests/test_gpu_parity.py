@@ -47,7 +47,7 @@ def _collect(eng, action, weights, root_value):
     return got
 
 
-ENGINES = [1, 2, 3, 4, 5]  # MZ_ENGINE_STEPWISE, _FUSED (best available), _FUSED_CTA, _FUSED_GROUP, _FUSED_LANE
+ENGINES = [1, 2, 3, 4, 5, 6]  # MZ_ENGINE_STEPWISE, _FUSED (best available), _FUSED_CTA, _GROUP, _LANE, _LANE2
 
 
 def _fused_or_skip(eng, engine_id, run):
