@@ -168,7 +168,9 @@ int mz_launch_count(mz_handle* h, int64_t* count);
 int mz_last_kernel_ms(mz_handle* h, float* ms);
 
 /* Evaluates include/mz_math.h device functions elementwise (bit-parity tests against the host build).
- * kind: 0 expf, 1 logf, 2 expm1f, 3 inv_scaling, 4 gumbel-from-bits (x reinterpreted as uint32). */
+ * kind: 0 expf, 1 logf, 2 expm1f, 3 inv_scaling, 4 gumbel-from-bits (x reinterpreted as uint32),
+ * 5 the kernels' batched fast division: x holds n (a, b) pairs, y[i] = a/b, or a marker NaN (0x7fc00001) where the
+ * kernels would fall back to the IEEE slow path. */
 int mz_math_probe(int32_t kind, const float* x_dev, float* y_dev, int64_t n, void* stream);
 
 #ifdef __cplusplus

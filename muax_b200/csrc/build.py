@@ -34,6 +34,8 @@ def build(force=False, verbose=False):
            "-o", OUT] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    for d in os.environ.get("MZ_NVCC_DEFINES", "").split():
+        cmd.insert(1, "-D" + d)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -39,7 +39,7 @@ constexpr uint32_t kNoChild = 0xFFFFu;
 template <int A, int E, int H, int S>
 struct L2Smem {  // float offsets of the CTA's shared memory
   static constexpr int F = 2 * S + 1;
-  int w, pbc, in, hA, hB, ns, rlog, vlog, plog, er, ev, nz, sc, blocks, total;
+  int w, pbc, in, hA, hB, ns, rlog, vlog, plog, er, ev, nz, sc, cold, blocks, total;
   __host__ __device__ L2Smem(int packed_floats, int NS, int obs_dim, int N) {
     int o = 0;
     w = o; o += round_up(packed_floats, 4);
@@ -55,6 +55,7 @@ struct L2Smem {  // float offsets of the CTA's shared memory
     ev = o; o += F * kLT;
     nz = o; o += 2 * kLT * kGNoiseFloats;
     sc = o; o += 3 * kLT;
+    cold = o; o += round_up(kLT * (A + 2), 4);
     blocks = o;
     total = o + kLT * L2Layout<A, E>(N).stride;
   }
@@ -142,8 +143,17 @@ __device__ __forceinline__ void l2_minmax_col(const float* raw_col, bool enabled
   }
   float scale = MZ_SUB(hi, lo);
   if (scale < 1e-5f) scale = MZ_ADD(scale, 1e-5f);
+  float num[N_];
+  bool bad = false;
 #pragma unroll
-  for (int k = 0; k < N_; ++k) v[k] = MZ_DIV(MZ_SUB(v[k], lo), scale);
+  for (int k = 0; k < N_; ++k) {
+    num[k] = MZ_SUB(v[k], lo);
+    v[k] = div_try(num[k], scale, bad);
+  }
+  if (bad) {
+#pragma unroll
+    for (int k = 0; k < N_; ++k) v[k] = MZ_DIV(num[k], scale);
+  }
 }
 
 template <int F>
@@ -162,15 +172,62 @@ __device__ __forceinline__ float l2_head_scalar(const float* e_col) {
   float s = 0.0f;
 #pragma unroll
   for (int j = 0; j < F; ++j) s = MZ_ADD(s, e[j]);
+  float pr[F];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < F; ++j) pr[j] = div_try(e[j], s, bad);
+  if (bad) {
+#pragma unroll
+    for (int j = 0; j < F; ++j) pr[j] = MZ_DIV(e[j], s);
+  }
   float x = 0.0f;
 #pragma unroll
-  for (int j = 0; j < F; ++j) x = MZ_ADD(x, MZ_MUL((float)(j - S), MZ_DIV(e[j], s)));
+  for (int j = 0; j < F; ++j) x = MZ_ADD(x, MZ_MUL((float)(j - S), pr[j]));
   return mz_inv_scaling(x);
 }
+
+// CTA barrier, or a named barrier over the first `nthreads` threads of a warp role when the roles are split.
+__device__ __forceinline__ void l2_bar(bool named, int id, int nthreads) {
+  if (named)
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+  else
+    __syncthreads();
+}
+
+// Cold path of the selection: tie-break noise for a level the pre-computed table does not cover (depth >= K, or
+// no table at all).  Kept out of line so the hot loop stays small.  k0/k1 carry the jax key chain between levels.
+// All state goes through this thread's shared-memory slot {key0, key1, noise[A]} (no stack frame).
+template <int A>
+__device__ __noinline__ void l2_noise_cold(const uint32_t* sim_key, uint32_t global_batch, uint32_t global_row,
+                                           int prng_mode, int depth, int K, const uint32_t* cont, float* slot) {
+  uint32_t k0 = __float_as_uint(slot[0]), k1 = __float_as_uint(slot[1]);
+  if (K < 0 && depth == 0) split_key(sim_key[0], sim_key[1], global_batch, global_row, prng_mode, k0, k1);
+  if (K >= 0 && depth == K) {
+    k0 = __ldg(cont);
+    k1 = __ldg(cont + 1);
+  }
+  uint32_t s0, s1;
+  lt_split2(k0, k1, prng_mode, k0, k1, s0, s1);
+  slot[0] = __uint_as_float(k0);
+  slot[1] = __uint_as_float(k1);
+#pragma unroll
+  for (int x = 0; x < A; ++x) slot[2 + x] = tie_break_noise(bits_word(s0, s1, A, x, prng_mode));
+}
+
+#ifdef MZ_PHASE_CLOCKS
+#define MZ_CLK(i) do { const long long t__ = clock64(); phase_acc[i] += t__ - phase_t; phase_t = t__; } while (0)
+#else
+#define MZ_CLK(i) do { } while (0)
+#endif
 
 template <int A, int E, int H, int S>
 __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
   constexpr int F = 2 * S + 1;
+#ifdef MZ_PHASE_CLOCKS
+  long long phase_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long phase_t = clock64();
+  const long long kernel_t0 = phase_t;
+#endif
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t wbar;
   const LaneNet& net = a.net;
@@ -199,11 +256,14 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
   float* blocks = smem + M.blocks;
 
   // ---- prologue
-  if (tid == 0) {
+  const bool use_tma = a.dump_tree < 2;  // debug knob (MZ_NO_TMA): stage the weights with plain loads instead
+  if (use_tma && tid == 0) {
     mbar_init(&wbar, 1);
     mbar_expect_tx(&wbar, (uint32_t)(round_up(net.packed_floats, 4) * 4));
     tma_bulk_g2s(w, a.packed, (uint32_t)(round_up(net.packed_floats, 4) * 4), &wbar);
   }
+  if (!use_tma)
+    for (int i = tid; i < round_up(net.packed_floats, 4); i += blockDim.x) w[i] = a.packed[i];
   for (int n = tid; n < NS + 2; n += blockDim.x) pbc[n] = pbc_explore((float)n, a.p.pb_c_init, a.p.pb_c_base);
   {  // tree init: zero everything; child records start as {kNoChild<<16, 0, 0, 0}; parents as 0xFFFFFFFF
     uint32_t* ub = reinterpret_cast<uint32_t*>(blocks);
@@ -219,7 +279,7 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
     const int tr = i / net.obs_dim, k = i - tr * net.obs_dim;
     bufIn[k * kLT + tr] = a.obs[(size_t)min(row0 + tr, a.B - 1) * net.obs_dim + k];
   }
-  mbar_wait(&wbar, 0);
+  if (use_tma) mbar_wait(&wbar, 0);
   __syncthreads();
 
   const int tpw = kLT / nwarps > 0 ? kLT / nwarps : 1;
@@ -342,36 +402,39 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
   __syncthreads();
 
   const int max_depth = p.max_depth > 0 ? p.max_depth : NS;
+  bool root_masked = false;
+  if (owner) {
+#pragma unroll
+    for (int x = 0; x < A; ++x) root_masked = root_masked || troot[A + x] != 0.0f;
+  }
+  // Warp roles inside recurrent_fn: "main" warps [0, MW) run the dense layers and the value head, "aux" warps
+  // [MW, nwarps) run the reward head concurrently (it only needs Dynamic's output), so it leaves the critical path.
+  const int MW = nwarps >= 16 ? 8 : nwarps;
+  const bool has_aux = nwarps > MW;
+  const int AW = nwarps - MW;
+  MZ_CLK(0);  // prologue + root
   // ---- simulations
   for (int sim = 0; sim < NS; ++sim) {
     int parent = 0, action = 0, next = 0;
     if (owner) {
       // simulate (A.3) with muzero_action_selection (A.5) + qtransform_by_parent_and_siblings (A.6)
       const float* row = nzbuf + ((size_t)(sim & 1) * kLT + ti) * kGNoiseFloats;
-      uint32_t k0 = 0, k1 = 0;
-      if (!use_table)
-        split_key(p.sim_keys[2 * sim], p.sim_keys[2 * sim + 1], (uint32_t)p.global_batch, (uint32_t)p.batch_offset,
-                  p.prng_mode, k0, k1);
+      float* slot = smem + M.cold + ti * (A + 2);
       int node = 0, depth = 0;
       for (;;) {
         const float4 nd = nodes[node];
         float4 ch[A];
 #pragma unroll
         for (int x = 0; x < A; ++x) ch[x] = childs[node * A + x];
-        float nz[A];
-        if (use_table && depth < a.K) {
-#pragma unroll
-          for (int x = 0; x < A; ++x) nz[x] = row[depth * A + x];
-        } else {
-          if (use_table && depth == a.K) {
-            k0 = __ldg(a.cont_keys + ((size_t)b * NS + sim) * 2);
-            k1 = __ldg(a.cont_keys + ((size_t)b * NS + sim) * 2 + 1);
-          }
-          uint32_t s0, s1;
-          lt_split2(k0, k1, p.prng_mode, k0, k1, s0, s1);
-#pragma unroll
-          for (int x = 0; x < A; ++x) nz[x] = tie_break_noise(bits_word(s0, s1, A, x, p.prng_mode));
+        const float* nzp = row + depth * A;
+        if (!(use_table && depth < a.K)) {
+          l2_noise_cold<A>(p.sim_keys + 2 * sim, (uint32_t)p.global_batch, (uint32_t)p.batch_offset, p.prng_mode, depth,
+                           use_table ? a.K : -1, use_table ? a.cont_keys + ((size_t)b * NS + sim) * 2 : nullptr, slot);
+          nzp = slot + 2;
         }
+        float nz[A];
+#pragma unroll
+        for (int x = 0; x < A; ++x) nz[x] = nzp[x];
         int vis[A];
         float q[A];
         float lo = nd.y, hi = nd.y;
@@ -379,29 +442,40 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
         for (int x = 0; x < A; ++x) {
           vis[x] = (int)(__float_as_uint(ch[x].x) & 0xFFFFu);
           q[x] = MZ_ADD(ch[x].w, MZ_MUL(gamma, ch[x].z));
-          if (vis[x] > 0) {
-            lo = fminf(lo, q[x]);
-            hi = fmaxf(hi, q[x]);
-          }
+          lo = vis[x] > 0 ? fminf(lo, q[x]) : lo;
+          hi = vis[x] > 0 ? fmaxf(hi, q[x]) : hi;
         }
         const float denom = fmaxf(MZ_SUB(hi, lo), 1e-8f);
-        int best = 0;
-        float bestv = 0.0f;
+        float vnum[A], pnum[A], pden[A], vsv[A], psv[A];
+        bool bad = false;
 #pragma unroll
         for (int x = 0; x < A; ++x) {
-          const float vs = MZ_DIV(MZ_SUB(vis[x] > 0 ? q[x] : lo, lo), denom);
-          const float ps = MZ_DIV(MZ_MUL(nd.z, ch[x].y), (float)(vis[x] + 1));
-          float s = MZ_ADD(MZ_ADD(vs, ps), nz[x]);
-          if (depth == 0 && troot[A + x] != 0.0f) s = -mz_inf();
-          if (x == 0 || s > bestv) {
-            bestv = s;
-            best = x;
+          vnum[x] = MZ_SUB(vis[x] > 0 ? q[x] : lo, lo);
+          pnum[x] = MZ_MUL(nd.z, ch[x].y);
+          pden[x] = (float)(vis[x] + 1);
+          vsv[x] = div_try(vnum[x], denom, bad);
+          psv[x] = div_try(pnum[x], pden[x], bad);
+        }
+        if (bad) {
+#pragma unroll
+          for (int x = 0; x < A; ++x) {
+            vsv[x] = MZ_DIV(vnum[x], denom);
+            psv[x] = MZ_DIV(pnum[x], pden[x]);
           }
         }
-        action = best;
-        uint32_t cx = __float_as_uint(ch[0].x);
+        int best = 0;
+        float bestv = 0.0f;
+        uint32_t cx = 0u;
 #pragma unroll
-        for (int x = 1; x < A; ++x) cx = best == x ? __float_as_uint(ch[x].x) : cx;
+        for (int x = 0; x < A; ++x) {
+          float s = MZ_ADD(MZ_ADD(vsv[x], psv[x]), nz[x]);
+          if (root_masked && depth == 0 && troot[A + x] != 0.0f) s = -mz_inf();
+          const bool better = x == 0 || s > bestv;
+          bestv = better ? s : bestv;
+          best = better ? x : best;
+          cx = better ? __float_as_uint(ch[x].x) : cx;
+        }
+        action = best;
         const uint32_t ci = cx >> 16;
         ++depth;
         if (ci == kNoChild || depth >= max_depth) {
@@ -416,19 +490,23 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
 #pragma unroll
       for (int e = 0; e < E; ++e) bufIn[e * kLT + ti] = temb[parent * E + e];
     }
+    MZ_CLK(1);  // select
     __syncthreads();
+    MZ_CLK(2);  // barrier after select
     // recurrent_fn (muax/model.py:265-282)
-    l2_layer1<E, H>(w, net.dyn_ns[0], net.dyn_r[0], bufIn, sc_action[lane], act_kind, hA, hB, lane, warp, nwarps);
+    if (warp < MW) l2_layer1<E, H>(w, net.dyn_ns[0], net.dyn_r[0], bufIn, sc_action[lane], act_kind, hA, hB, lane, warp, MW);
     __syncthreads();
+    MZ_CLK(3);  // dyn layer 1 + barrier
     l2_layer2<H, E, F>(w, net.dyn_ns[1], net.dyn_r[1], hA, hB, bufNs, bufR, lane, warp, nwarps);
     if (use_table && sim + 1 < NS) prefetch_noise(sim + 1, (sim + 1) & 1);
     __syncthreads();
-    {  // every warp normalises its lane's next state itself (no separate min-max phase); warp 0 publishes it
+    MZ_CLK(4);  // dyn layer 2 + barrier
+    if (warp < MW) {
+      // main warps: min-max (every warp for its own lane, in registers) -> Prediction -> value head
       float v[E];
       l2_minmax_col<E>(bufNs + lane, net.dyn_minmax != 0, v);
-      // pred layer 1 straight from registers
       constexpr int NB = H / 4;
-      for (int g = warp; g < 2 * NB; g += nwarps) {
+      for (int g = warp; g < 2 * NB; g += MW) {
         const bool second = g >= NB;
         const LLayer& Ld = second ? net.pred_pi[0] : net.pred_v[0];
         const int j0 = (second ? g - NB : g) * 4;
@@ -445,26 +523,38 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
                        activate(MZ_ADD(a2, bv.z), act_kind), activate(MZ_ADD(a3, bv.w), act_kind)};
         l2_store<H>((second ? hB : hA) + lane, j0, r4);
       }
-      if (warp == nwarps - 1) {
+      if (warp == MW - 1) {
 #pragma unroll
         for (int k = 0; k < E; ++k) bufIn[k * kLT + lane] = v[k];
       }
+      l2_bar(has_aux, 2, MW * 32);
+      MZ_CLK(5);  // min-max + pred layer 1 + barrier
+      l2_layer2<H, F, A>(w, net.pred_v[1], net.pred_pi[1], hA, hB, bufV, bufP, lane, warp, MW);
+      l2_bar(has_aux, 2, MW * 32);
+      MZ_CLK(6);  // pred layer 2 + barrier
+      if (has_aux) {
+        l2_head_exps<F>(bufV + lane, bufEv + lane, warp, MW);
+      } else {
+        const int half = MW / 2;
+        if (warp < half)
+          l2_head_exps<F>(bufR + lane, bufEr + lane, warp, half);
+        else
+          l2_head_exps<F>(bufV + lane, bufEv + lane, warp - half, MW - half);
+      }
+      l2_bar(has_aux, 2, MW * 32);
+      MZ_CLK(7);  // exps + barrier
+      if (warp == 0) sc_value[lane] = l2_head_scalar<F, S>(bufEv + lane);
+      if (!has_aux && warp == MW / 2) sc_reward[lane] = l2_head_scalar<F, S>(bufEr + lane);
+      MZ_CLK(8);  // head scalar
+    } else {
+      // aux warps: reward head, off the critical path
+      l2_head_exps<F>(bufR + lane, bufEr + lane, warp - MW, AW);
+      l2_bar(true, 1, AW * 32);
+      if (warp == MW) sc_reward[lane] = l2_head_scalar<F, S>(bufEr + lane);
     }
-    __syncthreads();
-    l2_layer2<H, F, A>(w, net.pred_v[1], net.pred_pi[1], hA, hB, bufV, bufP, lane, warp, nwarps);
-    __syncthreads();
-    {
-      const int half = nwarps / 2;
-      if (warp < half)
-        l2_head_exps<F>(bufR + lane, bufEr + lane, warp, half);
-      else
-        l2_head_exps<F>(bufV + lane, bufEv + lane, warp - half, nwarps - half);
-    }
-    __syncthreads();
-    if (warp == 0) sc_reward[lane] = l2_head_scalar<F, S>(bufEr + lane);
-    if (warp == nwarps / 2) sc_value[lane] = l2_head_scalar<F, S>(bufEv + lane);
     cp_async_wait_all();
     __syncthreads();
+    MZ_CLK(9);  // final barrier of recurrent_fn
     if (owner) {
       // expand (A.3)
       const float reward = sc_reward[ti], value = sc_value[ti];
@@ -480,11 +570,19 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
         ex[x] = mz_expf(MZ_SUB(lg[x], mx));
         sum = MZ_ADD(sum, ex[x]);
       }
+      float pb[A];
+      bool badp = false;
+#pragma unroll
+      for (int x = 0; x < A; ++x) pb[x] = div_try(ex[x], sum, badp);
+      if (badp) {
+#pragma unroll
+        for (int x = 0; x < A; ++x) pb[x] = MZ_DIV(ex[x], sum);
+      }
 #pragma unroll
       for (int x = 0; x < A; ++x) {
         tlog[next * A + x] = lg[x];
         float4 c = childs[next * A + x];
-        c.y = MZ_DIV(ex[x], sum);
+        c.y = pb[x];
         childs[next * A + x] = c;
       }
 #pragma unroll
@@ -511,7 +609,10 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
         const int ci = __float_as_int(pd.x);
         const float count = (float)ci;
         G_ = MZ_ADD(c.w, MZ_MUL(gamma, G_));
-        const float pv = MZ_DIV(MZ_ADD(MZ_MUL(pd.y, count), G_), MZ_ADD(count, 1.0f));
+        const float pnum = MZ_ADD(MZ_MUL(pd.y, count), G_), pden = MZ_ADD(count, 1.0f);
+        bool badb = false;
+        float pv = div_try(pnum, pden, badb);
+        if (badb) pv = MZ_DIV(pnum, pden);
         nodes[pn] = make_float4(__int_as_float(ci + 1), pv, pbc[min(ci + 1, NS + 1)], pd.w);
         c.x = __uint_as_float(__float_as_uint(c.x) + 1u);
         c.z = child_value;
@@ -520,7 +621,15 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
         index = pn;
       }
     }
+    MZ_CLK(10);  // expand + backup
   }
+#ifdef MZ_PHASE_CLOCKS
+  if (blockIdx.x == 1 && lane == 0 && (warp == 0 || warp == 3 || warp == nwarps - 1)) {
+    printf("warp %d total %lld | root %lld select %lld bar %lld dynL1 %lld dynL2 %lld mm+predL1 %lld predL2 %lld exps %lld "
+           "scalar %lld endbar %lld backup %lld\n", warp, clock64() - kernel_t0, phase_acc[0], phase_acc[1], phase_acc[2],
+           phase_acc[3], phase_acc[4], phase_acc[5], phase_acc[6], phase_acc[7], phase_acc[8], phase_acc[9], phase_acc[10]);
+  }
+#endif
 
   // ---- policy epilogue (A.2): visit_probs -> temperature -> categorical
   if (owner) {
@@ -631,7 +740,7 @@ inline const std::vector<Lane2Variant>& lane2_variants() {
 
 struct Lane2State {
   const Lane2Variant* variant = nullptr;
-  int warps = 8;
+  int warps = 16;
 };
 
 inline void lane2_init(Lane2State& st, const LaneState& ls, const Net& net, int max_smem) {
@@ -651,7 +760,7 @@ inline void lane2_init(Lane2State& st, const LaneState& ls, const Net& net, int 
       st.variant = &v;
     }
   if (const char* wv = getenv("MZ_LANE2_WARPS")) st.warps = atoi(wv);
-  if (st.warps != 4 && st.warps != 8 && st.warps != 16) st.warps = 8;
+  if (st.warps != 4 && st.warps != 8 && st.warps != 16) st.warps = 16;
 }
 
 inline bool lane2_supported(const Lane2State& st, const LaneState& ls, const SearchParams& p) {
@@ -680,6 +789,7 @@ inline int lane2_launch(Lane2State& st, LaneState& ls, const Tree& out, const Se
   a.B = B;
   a.N = N;
   a.dump_tree = getenv("MZ_FUSED_NO_DUMP") ? 0 : 1;
+  if (getenv("MZ_NO_TMA")) a.dump_tree = 2;
   a.K = std::min(16, kGNoiseFloats / A);
   if (const char* k = getenv("MZ_GROUP_K")) a.K = std::max(0, std::min(a.K, atoi(k)));
   if (NS > 0 && a.K > 0) {

@@ -271,13 +271,20 @@ __global__ void __launch_bounds__(kTreeThreads) finish_kernel(Tree t, SearchPara
 __global__ void math_probe_kernel(int kind, const float* x, float* y, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float v = x[i];
+  const float v = kind == 5 ? 0.0f : x[i];
   float r;
   switch (kind) {
     case 0: r = mz_expf(v); break;
     case 1: r = mz_logf(v); break;
     case 2: r = mz_expm1f(v); break;
     case 3: r = mz_inv_scaling(v); break;
+    case 5: {  // x holds (a, b) pairs for 2n inputs; this thread handles pair i (n = number of pairs)
+      const float a = x[2 * i], b = x[2 * i + 1];
+      bool bad = false;
+      r = div_try(a, b, bad);
+      r = bad ? __uint_as_float(0x7fc00001u) : r;  // marker NaN: "the kernels would take the IEEE slow path here"
+      break;
+    }
     default: r = mz_bits_to_gumbel(__float_as_uint(v)); break;
   }
   y[i] = r;

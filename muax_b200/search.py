@@ -237,11 +237,12 @@ class SearchEngine:
 
 def math_probe(kind, x):
     """Evaluates include/mz_math.h on the device (bit-parity tests).  kind: expf/logf/expm1f/inv_scaling/gumbel."""
-    kinds = {"expf": 0, "logf": 1, "expm1f": 2, "inv_scaling": 3, "gumbel": 4}
+    kinds = {"expf": 0, "logf": 1, "expm1f": 2, "inv_scaling": 3, "gumbel": 4, "fast_div": 5}
     lib = _lib.load()
     x = x.contiguous()
-    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    n = x.numel() // 2 if kind == "fast_div" else x.numel()   # fast_div: x is [n, 2] = (a, b) pairs
+    y = torch.empty(n, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(lib.mz_math_probe(kinds[kind], _ptr(x), _ptr(y), x.numel(), stream), "mz_math_probe")
-    return y
+        _lib.check(lib.mz_math_probe(kinds[kind], _ptr(x), _ptr(y), n, stream), "mz_math_probe")
+    return y if kind == "fast_div" else y.reshape(x.shape)

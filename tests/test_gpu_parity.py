@@ -75,6 +75,32 @@ def test_device_math_is_bit_identical_to_host_build(c_oracle):
         assert np.array_equal(y.view(np.uint32), host[kind](x).view(np.uint32)), kind
 
 
+def test_fast_division_matches_ieee():
+    """The fused engines replace `__fdiv_rn` by its fast-path sequence issued in batches, with one cold IEEE branch
+    when an operand is outside the safe exponent window.  Wherever the fast path is taken it must equal IEEE
+    division (NumPy float32) bit for bit: random operands over the window, the ranges the search produces
+    (probabilities, visit counts, value spreads), exact quotients and near-halfway quotients."""
+    from muax_b200.search import math_probe
+    rng = np.random.default_rng(0)
+    n = 4_000_000
+    a = np.concatenate([
+        (rng.standard_normal(n) * np.exp2(rng.uniform(-29, 29, n))).astype(np.float32),
+        rng.uniform(0, 1, n).astype(np.float32), (rng.uniform(0, 60, n) * rng.uniform(0, 1, n)).astype(np.float32),
+        (rng.integers(1, 2**24, n) * rng.integers(1, 64, n)).astype(np.float32), np.zeros(16, np.float32)])
+    b = np.concatenate([
+        (rng.standard_normal(n) * np.exp2(rng.uniform(-29, 29, n))).astype(np.float32),
+        rng.integers(1, 300, n).astype(np.float32), np.maximum(rng.uniform(0, 20, n), 1e-8).astype(np.float32),
+        rng.integers(1, 64, n).astype(np.float32), np.arange(1, 17, dtype=np.float32)])
+    b[b == 0] = 1.0
+    pairs = np.stack([a, b], axis=1)
+    got = math_probe("fast_div", torch.from_numpy(pairs).cuda()).cpu().numpy()
+    slow = got.view(np.uint32) == 0x7FC00001
+    assert slow.mean() < 0.05          # the window covers what the search feeds it
+    with np.errstate(all="ignore"):
+        want = (a / b).astype(np.float32)
+    assert np.array_equal(got[~slow].view(np.uint32), want[~slow].view(np.uint32))
+
+
 @pytest.mark.parametrize("engine_id", ENGINES)
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_vectors(name, engine_id):
