@@ -38,6 +38,13 @@ WORKLOADS = {
                                              policy=0, qtransform=0, minmax=1),
     "lunarlander_gumbel_e64_b4096_sim32": dict(obs_dim=8, E=64, A=4, S=10, hidden=(16,), batch=4096, num_sim=32,
                                                policy=1, qtransform=0, minmax=1),
+    # examples/lunarlander.ipynb cell 2-3: 64-64-16 ELU stacks, no min-max, support 20
+    "lunarlander_notebook_e64_b4096_sim200": dict(obs_dim=8, E=64, A=4, S=20, hidden=(64, 64, 16), batch=4096,
+                                                  num_sim=200, policy=0, qtransform=0, minmax=0),
+    # C5 per-GPU shard: 1024 trees, A=18, E=H=256; the flat 256-wide "observation" stands in for the conv torso's
+    # output (the conv root representation runs once per act outside the search loop)
+    "atari_mlp_e256_b1024_sim50": dict(obs_dim=256, E=256, A=18, S=10, hidden=(256,), batch=1024, num_sim=50,
+                                       policy=0, qtransform=0, minmax=1),
 }
 DEFAULT_WORKLOAD = "cartpole_mlp_e8_b4096_sim50"
 
@@ -188,7 +195,8 @@ def run_ours(args, wl, name):
     eng.set_weights(blob)
     engine_id = {"auto": _lib.ENGINE_AUTO, "stepwise": _lib.ENGINE_STEPWISE, "fused": _lib.ENGINE_FUSED,
                  "fused_cta": _lib.ENGINE_FUSED_CTA, "fused_group": _lib.ENGINE_FUSED_GROUP,
-                 "fused_lane": _lib.ENGINE_FUSED_LANE, "fused_lane2": _lib.ENGINE_FUSED_LANE2}[args.engine]
+                 "fused_lane": _lib.ENGINE_FUSED_LANE, "fused_lane2": _lib.ENGINE_FUSED_LANE2,
+                 "resident": _lib.ENGINE_RESIDENT}[args.engine]
     obs_all = np.random.default_rng(1).standard_normal((GB, wl["obs_dim"])).astype(np.float32)
     obs_host = np.ascontiguousarray(obs_all[rank * B:(rank + 1) * B])
     obs_dev = torch.from_numpy(obs_host).to(dev)
@@ -305,7 +313,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "stepwise", "fused", "fused_cta", "fused_group", "fused_lane", "fused_lane2"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "stepwise", "fused", "fused_cta", "fused_group", "fused_lane", "fused_lane2", "resident"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libmzsearch.so")
 SOURCES = [os.path.join(HERE, "mzsearch.cu")]
-DEPS = SOURCES + [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_fused.cuh", "mz_group.cuh", "mz_lane.cuh", "mz_lane2.cuh")] + [
+DEPS = SOURCES + [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_fused.cuh", "mz_group.cuh", "mz_lane.cuh", "mz_lane2.cuh", "mz_resident.cuh")] + [
     os.path.join(ROOT, "include", f) for f in ("mz_math.h", "mzsearch.h")]
 
 

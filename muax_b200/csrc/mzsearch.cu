@@ -20,6 +20,7 @@
 #include "mz_group.cuh"
 #include "mz_lane.cuh"
 #include "mz_lane2.cuh"
+#include "mz_resident.cuh"
 
 namespace mz {
 
@@ -331,6 +332,7 @@ struct mz_handle {
   mz::GroupState group;
   mz::LaneState lanes;
   mz::Lane2State lane2;
+  mz::ResidentState resident;
 };
 
 namespace mz {
@@ -556,14 +558,30 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   const bool group_ok = have_w && group_supported(h->group, h->params, h->cfg.batch);
   const bool fused_ok = have_w && fused_supported(h->fused, h->net, h->params);
   const bool lane2_ok = lane_ok && lane2_supported(h->lane2, h->lanes, h->params);
+  const bool resident_ok = h->weights != nullptr && resident_supported(h->resident, h->net, h->cfg.batch);
   enum { kLane = 100, kLane2 = 101 };
-  if (engine == MZ_ENGINE_AUTO) engine = (lane_ok || group_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE;
-  // best fused variant first: measured on B200 (profiles/): group 0.78 ms, lane 0.99 ms, CTA-phased 1.5 ms per act
+  // AUTO: the shared-memory engines when the trees fit on chip (measured on B200, profiles/: lane2 0.48 ms, group
+  // 0.72 ms per act at the headline shapes), else the CTA-resident engine (trees in HBM/L2, one launch per act);
+  // the stepwise engine remains for the callback mode and as the reference implementation of the kernels.
+  if (engine == MZ_ENGINE_AUTO)
+    engine = (lane2_ok || group_ok) ? MZ_ENGINE_FUSED
+                                    : (resident_ok ? MZ_ENGINE_RESIDENT
+                                                   : ((lane_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE));
   if (engine == MZ_ENGINE_FUSED)
     engine = lane2_ok ? (int)kLane2 : (group_ok ? MZ_ENGINE_FUSED_GROUP : (lane_ok ? (int)kLane : MZ_ENGINE_FUSED_CTA));
   if (engine == MZ_ENGINE_FUSED_LANE) engine = kLane;
   if (engine == MZ_ENGINE_FUSED_LANE2) engine = kLane2;
-  if (engine == kLane || engine == kLane2 || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
+  if (engine == MZ_ENGINE_RESIDENT) {
+    if (!resident_ok) return fail("the resident engine does not support this configuration (see DESIGN.md)");
+    if (obs != nullptr && h->cfg.obs_dim <= 0)
+      return fail("handle was created with obs_dim = 0: supply the root embedding instead of obs");
+    h->has_invalid = invalid != nullptr;
+    std::string err;
+    if (resident_launch(h->resident, h->net, h->weights, h->tree, h->params, obs, root_emb, root_logits, root_value,
+                        invalid, noise, action_out, weights_out, root_value_out, stream, &err))
+      return fail(err);
+    h->launches += 1;
+  } else if (engine == kLane || engine == kLane2 || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
     if ((engine == MZ_ENGINE_FUSED_CTA && !fused_ok) || (engine == MZ_ENGINE_FUSED_GROUP && !group_ok) ||
         (engine == kLane && !lane_ok) || (engine == kLane2 && !lane2_ok))
       return fail("the fused engine does not support this configuration (see DESIGN.md)");
@@ -760,7 +778,8 @@ int mz_create(mz_handle** out, const mz_config* cfg) {
   {
     std::string err;
     if (fused_init(h->fused, h->net, cfg->batch, cfg->max_num_simulations, cfg->device, &err) ||
-        group_init(h->group, h->net, cfg->device, &err) || lane_init(h->lanes, h->net, cfg->device, &err)) {
+        group_init(h->group, h->net, cfg->device, &err) || lane_init(h->lanes, h->net, cfg->device, &err) ||
+        resident_init(h->resident, h->net, cfg->device, &err)) {
       mz_destroy(h);
       return fail(err);
     }

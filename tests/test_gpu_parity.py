@@ -47,7 +47,7 @@ def _collect(eng, action, weights, root_value):
     return got
 
 
-ENGINES = [1, 2, 3, 4, 5, 6]  # MZ_ENGINE_STEPWISE, _FUSED (best available), _FUSED_CTA, _GROUP, _LANE, _LANE2
+ENGINES = [1, 2, 3, 4, 5, 6, 7]  # MZ_ENGINE_STEPWISE, _FUSED (best available), _FUSED_CTA, _GROUP, _LANE, _LANE2, _RESIDENT
 
 
 def _fused_or_skip(eng, engine_id, run):
@@ -173,10 +173,11 @@ def test_root_supplied_by_caller():
     model = np_mctx.Model(nets, np_mctx.ExactMath(), cfg["support_size"])
     logits, value, emb = model.root_inference(inp["obs"])
     eng = _engine(nets, inp["obs"].shape[0], cfg, cfg["num_simulations"])
-    for root in ((logits, value, emb), (None, None, emb)):
-        out = eng.search(inp["key"], root=root, noise=inp["noise"], **_search_kwargs(cfg))
-        got = _collect(eng, *out)
-        assert_same_search(got, want)
+    for engine_id in (1, 7):  # the engines that accept a caller-made root: stepwise and CTA-resident
+        for root in ((logits, value, emb), (None, None, emb)):
+            out = eng.search(inp["key"], root=root, noise=inp["noise"], engine=engine_id, **_search_kwargs(cfg))
+            got = _collect(eng, *out)
+            assert_same_search(got, want)
 
 
 def test_callback_mode_reproduces_native_search():
