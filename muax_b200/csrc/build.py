@@ -1,17 +1,31 @@
 """Builds muax_b200/libmzsearch.so in-tree with nvcc for sm_100a (no torch involved: the library is plain
-CUDA runtime + the C ABI of include/mzsearch.h)."""
+CUDA runtime + the C ABI of include/mzsearch.h).  One object per translation unit, compiled in parallel and
+cached under csrc/_obj/ (stale objects are detected through the header mtimes)."""
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libmzsearch.so")
-SOURCES = [os.path.join(HERE, "mzsearch.cu")]
-DEPS = SOURCES + [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_fused.cuh", "mz_group.cuh", "mz_lane.cuh", "mz_lane2.cuh", "mz_resident.cuh")] + [
+OBJ_DIR = os.path.join(HERE, "_obj")
+HEADERS = [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_fused.cuh", "mz_group.cuh", "mz_lane.cuh",
+                                            "mz_lane2.cuh", "mz_resident.cuh")] + [
     os.path.join(ROOT, "include", f) for f in ("mz_math.h", "mzsearch.h")]
+# translation unit -> the headers it includes (a TU is rebuilt when it or one of these is newer than its object)
+UNITS = {
+    "mzsearch.cu": HEADERS,
+    "mz_resident.cu": [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_resident.cuh")] + [
+        os.path.join(ROOT, "include", f) for f in ("mz_math.h", "mzsearch.h")],
+}
+SOURCES = [os.path.join(HERE, u) for u in UNITS]
+DEPS = SOURCES + HEADERS
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off"]
 
 
 def nvcc_path():
@@ -25,23 +39,39 @@ def up_to_date():
     return os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(p) for p in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
-        return OUT
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-           "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "--cudart=static",
-           "-o", OUT] + SOURCES
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    for d in os.environ.get("MZ_NVCC_DEFINES", "").split():
-        cmd.insert(1, "-D" + d)
+def _defines():
+    return ["-D" + d for d in os.environ.get("MZ_NVCC_DEFINES", "").split()]
+
+
+def _compile(unit, force, verbose):
+    src = os.path.join(HERE, unit)
+    tag = "".join(sorted(os.environ.get("MZ_NVCC_DEFINES", "").split()))
+    obj = os.path.join(OBJ_DIR, unit.replace(".cu", (("." + tag) if tag else "") + ".o"))
+    deps = [src] + UNITS[unit]
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(p) for p in deps):
+        return obj, ""
+    cmd = [nvcc_path()] + NVCC_FLAGS + _defines() + (["-Xptxas=-v"] if verbose else []) + ["-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libmzsearch.so")
+        raise RuntimeError(f"nvcc failed compiling {unit}")
+    return obj, res.stdout + res.stderr
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return OUT
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
+        results = list(pool.map(lambda u: _compile(u, force, verbose), UNITS))
+    objs = [o for o, _ in results]
+    res = subprocess.run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart=static",
+                          "-Xcompiler", "-fPIC", "-o", OUT] + objs, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libmzsearch.so")
     if verbose:
-        print(res.stdout + res.stderr)
+        print("".join(log for _, log in results))
     return OUT
 
 

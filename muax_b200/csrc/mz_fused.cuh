@@ -41,7 +41,6 @@ struct FusedLayout {  // offsets in floats from the dynamic smem base
   int weights, node_i, child_i, node_f, child_f, emb, noise, invalid, mlp, sel, total_floats;
 };
 
-__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 __host__ __device__ inline FusedLayout fused_layout(int weight_bytes, int T, int N, int A, int E, int ld) {
   FusedLayout L;
@@ -58,32 +57,6 @@ __host__ __device__ inline FusedLayout fused_layout(int weight_bytes, int T, int
   L.sel = off;     off += 5 * T + 4;          // parent, action, next, reward, value
   L.total_floats = round_up(off, 4);
   return L;
-}
-
-// ---- TMA bulk copy (global -> shared) with mbarrier completion --------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tMZ_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra MZ_DONE;\n\tbra MZ_WAIT;\n\tMZ_DONE:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
 }
 
 // Two hk.Sequential heads that read the same input, evaluated in lockstep: one barrier per layer instead of two.

@@ -558,7 +558,7 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   const bool group_ok = have_w && group_supported(h->group, h->params, h->cfg.batch);
   const bool fused_ok = have_w && fused_supported(h->fused, h->net, h->params);
   const bool lane2_ok = lane_ok && lane2_supported(h->lane2, h->lanes, h->params);
-  const bool resident_ok = h->weights != nullptr && resident_supported(h->resident, h->net, h->cfg.batch);
+  const bool resident_ok = h->weights != nullptr && resident_supported(h->resident, h->net, h->cfg.batch, h->params.num_simulations);
   enum { kLane = 100, kLane2 = 101 };
   // AUTO: the shared-memory engines when the trees fit on chip (measured on B200, profiles/: lane2 0.48 ms, group
   // 0.72 ms per act at the headline shapes), else the CTA-resident engine (trees in HBM/L2, one launch per act);
@@ -578,9 +578,8 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
     h->has_invalid = invalid != nullptr;
     std::string err;
     if (resident_launch(h->resident, h->net, h->weights, h->tree, h->params, obs, root_emb, root_logits, root_value,
-                        invalid, noise, action_out, weights_out, root_value_out, stream, &err))
+                        invalid, noise, action_out, weights_out, root_value_out, stream, &h->launches, &err))
       return fail(err);
-    h->launches += 1;
   } else if (engine == kLane || engine == kLane2 || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
     if ((engine == MZ_ENGINE_FUSED_CTA && !fused_ok) || (engine == MZ_ENGINE_FUSED_GROUP && !group_ok) ||
         (engine == kLane && !lane_ok) || (engine == kLane2 && !lane2_ok))
@@ -797,6 +796,7 @@ int mz_destroy(mz_handle* h) {
   mz::fused_destroy(h->fused);
   mz::group_destroy(h->group);
   mz::lane_destroy(h->lanes);
+  mz::resident_destroy(h->resident);
   for (void* p : h->allocs) cudaFree(p);
   if (h->weights) cudaFree(h->weights);
   if (h->table_dev) cudaFree(h->table_dev);
