@@ -272,69 +272,240 @@ __global__ void __launch_bounds__(128) resident_noise_kernel(SearchParams p, int
   cont[2 * (size_t)idx + 1] = k1;
 }
 
-// ------------------------------------------------------------------------------------------ expand + backup
+// ------------------------------------------------------------------------------------------ tree records
+// Working layout of the trees in HBM: 16-byte records, so that one level of `simulate` is one node load plus one
+// (MuZero) or two (Gumbel: + prior logit) 16-byte loads per lane, one level of `backward` two loads and two stores,
+// and every field of a node sits at a constant offset from one address.
+//   node  n        : { visits (int), node_value, raw_value, parent << 8 | action  (0xFFFFFFFF: none) }
+//   child (n, a) h0: { child index << 16 | visits  (index 0xFFFF: unvisited), prior prob, value, reward }
+//   child (n, a) h1: { prior logit, -, -, - }
+// children_discounts is not stored: on this path it is the constant gamma for every expanded edge (model.py:275) and
+// an unexpanded edge has reward = value = 0, so reward + gamma * value is the same +0 as mctx's 0 + 0 * 0.
+// The mctx SoA view of the C ABI (mz_get_tree) is produced on demand by resident_unpack_kernel.
 
-// `expand` scatter (A.3) + `backward` for one tree, walking the path recorded by the selection instead of chasing
-// parents[] / action_from_parent[]: the operands of level d-1 are loaded while level d's mean update is computed.
+constexpr uint32_t kRecNoChild = 0xFFFFu;
+constexpr uint32_t kRecNoParent = 0xFFFFFFFFu;
+
+struct RecTrees {    // the records of the trees one CTA owns (local tree index 0..R-1)
+  float4* nodes;     // [R][N]
+  float4* childs;    // [R][N][A][2]
+  float* emb;        // [R][N][E]  (the handle's SoA embeddings)
+  float* root_noise; // [R][A]
+  uint8_t* root_invalid;
+  int32_t* sim_depth; // [R][NS]
+  int32_t N, A, E;    // N = record stride (nodes of this search)
+  int32_t embN;       // node stride of the embeddings (the handle's capacity)
+};
+
+__device__ __forceinline__ ChildRow rec_child_row(const float4& h0, float logit, float gamma, bool ok) {
+  ChildRow c;
+  c.visits = ok ? (int)(__float_as_uint(h0.x) & 0xFFFFu) : 0;
+  c.logit = ok ? logit : 0.0f;
+  c.prob = ok ? h0.y : 0.0f;
+  c.value = ok ? h0.z : 0.0f;
+  c.reward = ok ? h0.w : 0.0f;
+  c.discount = ok ? gamma : 0.0f;
+  return c;
+}
+
+// Policy prologue (A.2 / A.4) + instantiate_tree_from_root (A.3) for one tree.
 template <int G>
-__device__ __forceinline__ void resident_expand_backup(const Tree& t, int b, int parent, int action, int next,
-                                                       float reward, float discount, float value, float logit_a,
-                                                       const float* next_emb, int a, unsigned m, const uint32_t* path,
-                                                       int depth) {
+__device__ __forceinline__ void rec_begin(const RecTrees& t, const SearchParams& p, int b, long gb,
+                                          const float* root_logits, float root_value, const float* root_emb,
+                                          const uint8_t* invalid, const float* noise, int a, unsigned m) {
+  const int A = t.A;
+  float logit, prob, nz;
+  bool inv;
+  group_begin_compute<G>(p, A, gb, root_logits, invalid, noise, a, m, logit, prob, nz, inv);
+  float4* ch = t.childs + (size_t)b * t.N * A * 2;
+  if (a < A) {
+    ch[a * 2] = make_float4(__uint_as_float(kRecNoChild << 16), prob, 0.0f, 0.0f);
+    ch[a * 2 + 1] = make_float4(logit, 0.0f, 0.0f, 0.0f);
+    t.root_noise[b * A + a] = nz;
+    t.root_invalid[b * A + a] = inv ? 1 : 0;
+  }
+  float* emb = t.emb + (size_t)b * t.embN * t.E;
+  for (int e = a; e < t.E; e += G) emb[e] = root_emb[e];
+  if (a == 0)
+    t.nodes[(size_t)b * t.N] = make_float4(__int_as_float(1), root_value, root_value, __uint_as_float(kRecNoParent));
+}
+
+// `simulate` (A.3) for one tree.  `fresh`: the selected edge was unvisited (the new node gets index sim + 1).
+template <int G>
+__device__ __forceinline__ void rec_simulate(const RecTrees& t, const SearchParams& p, int b, int sim, int a, unsigned m,
+                                             int& parent, int& action, int& next, int& depth_out, bool& fresh,
+                                             const SelectAux& aux, uint32_t* path) {
   const int A = t.A;
   const bool ok = a < A;
-  const long tb = (long)b * t.N;
+  const bool muzero = p.policy == MZ_POLICY_MUZERO;
+  const bool table = aux.noise_row != nullptr;
+  uint32_t k0 = 0, k1 = 0;
+  if (muzero && !table)
+    split_key(p.sim_keys[2 * sim], p.sim_keys[2 * sim + 1], (uint32_t)p.global_batch, (uint32_t)(p.batch_offset + b),
+              p.prng_mode, k0, k1);
+  const int max_depth = p.max_depth > 0 ? p.max_depth : p.num_simulations;
+  const float4* nodes = t.nodes + (size_t)b * t.N;
+  const float4* ch = t.childs + (size_t)b * t.N * A * 2;
+  const bool root_inv = ok && t.root_invalid[b * A + a] != 0;
+  const float root_gumbel = (!muzero && ok) ? t.root_noise[b * A + a] : 0.0f;
+  int node = 0, depth = 0;
+  uint32_t ci;
+  for (;;) {
+    const float4 nd = nodes[node];
+    float4 h0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float logit = 0.0f;
+    if (ok) {
+      h0 = ch[(node * A + a) * 2];
+      if (!muzero) logit = ch[(node * A + a) * 2 + 1].x;
+    }
+    uint32_t s0 = 0, s1 = 0;
+    bool have_noise = false;
+    float nz = 0.0f;
+    if (muzero) {
+      if (table && depth < aux.K) {
+        have_noise = true;
+        nz = aux.noise_row[depth * A + (ok ? a : 0)];
+      } else {
+        if (table && depth == aux.K) {
+          k0 = aux.cont0;
+          k1 = aux.cont1;
+        }
+        group_split2<G>(k0, k1, p.prng_mode, a, m, k0, k1, s0, s1);
+      }
+    }
+    const ChildRow c = rec_child_row(h0, logit, p.discount, ok);
+    action = group_select_score<G>(p, A, c, ok, nd.y, nd.z, __float_as_int(nd.x), depth, root_inv, root_gumbel, s0, s1, a,
+                                   m, have_noise, nz, aux.pbc);
+    ci = __shfl_sync(m, __float_as_uint(h0.x) >> 16, action, G);
+    if (a == 0) path[depth] = ((uint32_t)node << 8) | (uint32_t)action;
+    ++depth;
+    if (ci == kRecNoChild || depth >= max_depth) break;
+    node = (int)ci;
+  }
+  parent = node;
+  depth_out = depth;
+  fresh = ci == kRecNoChild;
+  next = fresh ? sim + 1 : (int)ci;
+}
+
+// `expand` scatter (A.3) + `backward` for one tree, walking the path recorded by the selection: the records of
+// level d-1 are loaded while level d's mean update is computed.
+template <int G>
+__device__ __forceinline__ void rec_expand_backup(const RecTrees& t, int b, int parent, int action, int next, bool fresh,
+                                                  float reward, float gamma, float value, float logit_a,
+                                                  const float* next_emb, int a, unsigned m, const uint32_t* path,
+                                                  int depth) {
+  const int A = t.A;
+  const bool ok = a < A;
+  float4* nodes = t.nodes + (size_t)b * t.N;
+  float4* ch = t.childs + (size_t)b * t.N * A * 2;
   const float prob = group_softmax<G>(logit_a, ok, A, m);
   if (ok) {
-    t.children_prior_logits[(tb + next) * A + a] = logit_a;
-    t.children_prior_probs[(tb + next) * A + a] = prob;
+    float4 h0 = make_float4(__uint_as_float(kRecNoChild << 16), prob, 0.0f, 0.0f);
+    if (!fresh) {  // max_depth re-expansion: priors are overwritten, the edge statistics stay (update_tree_node)
+      h0 = ch[(next * A + a) * 2];
+      h0.y = prob;
+    }
+    ch[(next * A + a) * 2] = h0;
+    ch[(next * A + a) * 2 + 1] = make_float4(logit_a, 0.0f, 0.0f, 0.0f);
   }
-  for (int e = a; e < t.E; e += G) t.embeddings[(tb + next) * t.E + e] = next_emb[e];
+  float* emb = t.emb + ((size_t)b * t.embN + next) * t.E;
+  for (int e = a; e < t.E; e += G) emb[e] = next_emb[e];
   if (a == 0) {
-    t.node_visits[tb + next] += 1;
-    t.raw_values[tb + next] = value;
-    t.node_values[tb + next] = value;
-    const long edge = (tb + parent) * A + action;
-    t.children_index[edge] = next;
-    t.children_rewards[edge] = reward;
-    t.children_discounts[edge] = discount;
-    t.parents[tb + next] = parent;
-    t.action_from_parent[tb + next] = action;
+    const int old_visits = fresh ? 0 : __float_as_int(nodes[next].x);
+    nodes[next] = make_float4(__int_as_float(old_visits + 1), value, value,
+                              __uint_as_float(((uint32_t)parent << 8) | (uint32_t)action));
     // backward: path[d] = (node << 8 | action) of the edge selected at depth d; path[depth - 1] = (parent, action)
     float G_ = value, child_value = value;
     int d = depth - 1;
-    long e2 = edge;
-    long pn = tb + parent;
-    int count_i = t.node_visits[pn];
-    float nv = t.node_values[pn];
-    float rw = reward, dc = discount;
-    int cv = t.children_visits[e2];
+    int pn = parent, e2 = (parent * A + action) * 2;
+    float4 nd = nodes[pn];
+    float4 c = ch[e2];
+    c.x = __uint_as_float(((uint32_t)next << 16) | (__float_as_uint(c.x) & 0xFFFFu));  // children_index[parent, action]
+    c.w = reward;                                                                      // children_rewards[parent, action]
     for (;;) {
-      long n_e2 = 0, n_pn = 0;
-      int n_count = 0, n_cv = 0;
-      float n_nv = 0.0f, n_rw = 0.0f, n_dc = 0.0f;
+      int n_pn = 0, n_e2 = 0;
+      float4 n_nd = nd, n_c = c;
       if (d > 0) {
         const uint32_t pa = path[d - 1];
-        n_pn = tb + (long)(pa >> 8);
-        n_e2 = n_pn * A + (long)(pa & 0xffu);
-        n_count = t.node_visits[n_pn];
-        n_nv = t.node_values[n_pn];
-        n_rw = t.children_rewards[n_e2];
-        n_dc = t.children_discounts[n_e2];
-        n_cv = t.children_visits[n_e2];
+        n_pn = (int)(pa >> 8);
+        n_e2 = (n_pn * A + (int)(pa & 0xffu)) * 2;
+        n_nd = nodes[n_pn];
+        n_c = ch[n_e2];
       }
+      const int count_i = __float_as_int(nd.x);
       const float count = (float)count_i;
-      G_ = MZ_ADD(rw, MZ_MUL(dc, G_));
-      const float pv = MZ_DIV(MZ_ADD(MZ_MUL(nv, count), G_), MZ_ADD(count, 1.0f));
-      t.node_values[pn] = pv;
-      t.node_visits[pn] = count_i + 1;
-      t.children_values[e2] = child_value;
-      t.children_visits[e2] = cv + 1;
+      G_ = MZ_ADD(c.w, MZ_MUL(gamma, G_));
+      const float pv = MZ_DIV(MZ_ADD(MZ_MUL(nd.y, count), G_), MZ_ADD(count, 1.0f));
+      nodes[pn] = make_float4(__int_as_float(count_i + 1), pv, nd.z, nd.w);
+      c.x = __uint_as_float(__float_as_uint(c.x) + 1u);  // children_visits += 1 (low 16 bits)
+      c.z = child_value;
+      ch[e2] = c;
       child_value = pv;
       if (d == 0) break;
       --d;
-      e2 = n_e2; pn = n_pn; count_i = n_count; nv = n_nv; rw = n_rw; dc = n_dc; cv = n_cv;
+      pn = n_pn; e2 = n_e2; nd = n_nd; c = n_c;
     }
+  }
+}
+
+// Policy epilogue for one tree (A.2 / A.4).
+template <int G>
+__device__ __forceinline__ void rec_finish(const RecTrees& t, const SearchParams& p, int b, long gb, bool has_invalid,
+                                           int a, unsigned m, int& action, float& weight) {
+  const int A = t.A;
+  const bool ok = a < A;
+  const bool muzero = p.policy == MZ_POLICY_MUZERO;
+  const float4* ch = t.childs + (size_t)b * t.N * A * 2;
+  const float4 nd = t.nodes[(size_t)b * t.N];
+  float4 h0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  float logit = 0.0f;
+  if (ok) {
+    h0 = ch[a * 2];
+    if (!muzero) logit = ch[a * 2 + 1].x;
+  }
+  const ChildRow c = rec_child_row(h0, logit, p.discount, ok);
+  const bool root_inv = !muzero && ok && t.root_invalid[b * A + a] != 0;
+  const float root_gumbel = (!muzero && ok) ? t.root_noise[b * A + a] : 0.0f;
+  group_finish_score<G>(p, A, c, ok, nd.y, nd.z, root_inv, root_gumbel, gb, has_invalid, a, m, action, weight);
+}
+
+// Records -> the mctx SoA arrays of the handle (mz_get_tree view).  One thread per (tree, node); nodes that were
+// never expanded (visits == 0) read as mctx's initial state (A.1).
+__global__ void __launch_bounds__(256) resident_unpack_kernel(const float4* __restrict__ nodes,
+                                                             const float4* __restrict__ childs, Tree o, int N_used,
+                                                             float gamma) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)o.B * o.N) return;
+  const int A = o.A;
+  const int n = (int)(i % o.N);
+  const long rec = (i / o.N) * N_used + n;  // records are packed with the stride of the search that wrote them
+  float4 nd = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(kRecNoParent));
+  if (n < N_used) nd = nodes[rec];
+  const int visits = __float_as_int(nd.x);
+  const uint32_t pa = __float_as_uint(nd.w);
+  o.node_visits[i] = visits;
+  o.parents[i] = pa == kRecNoParent ? -1 : (int)(pa >> 8);
+  o.action_from_parent[i] = pa == kRecNoParent ? -1 : (int)(pa & 0xFFu);
+  o.raw_values[i] = visits > 0 ? nd.z : 0.0f;
+  o.node_values[i] = visits > 0 ? nd.y : 0.0f;
+  for (int x = 0; x < A; ++x) {
+    const long g = i * A + x;
+    float4 h0 = make_float4(__uint_as_float(kRecNoChild << 16), 0.0f, 0.0f, 0.0f);
+    float logit = 0.0f;
+    if (visits > 0) {
+      h0 = childs[(rec * A + x) * 2];
+      logit = childs[(rec * A + x) * 2 + 1].x;
+    }
+    const uint32_t cx = __float_as_uint(h0.x);
+    const bool has = (cx >> 16) != kRecNoChild;
+    o.children_index[g] = has ? (int)(cx >> 16) : -1;
+    o.children_visits[g] = (int)(cx & 0xFFFFu);
+    o.children_prior_logits[g] = logit;
+    o.children_prior_probs[g] = h0.y;
+    o.children_values[g] = h0.z;
+    o.children_rewards[g] = h0.w;
+    o.children_discounts[g] = has ? gamma : 0.0f;
   }
 }
 
@@ -344,7 +515,9 @@ struct ResidentArgs {
   Net net;
   const float* weights;  // global fp32 blob
   int32_t weight_bytes;  // multiple of 16
-  Tree t;                // the handle's SoA tree (whole batch)
+  Tree t;                // the handle's SoA tree (embeddings, root_noise, root_invalid, sim_depth are used in place)
+  float4* rec_nodes;     // [B][N]
+  float4* rec_childs;    // [B][N][A][2]
   SearchParams p;
   const float* obs;          // [B,obs_dim] or null
   const float* root_emb;     // [B,E] when obs is null
@@ -376,24 +549,10 @@ __host__ __device__ inline ResidentLayout resident_layout(int weight_bytes_in_sm
   L.weights = off; off += round_up(weight_bytes_in_smem / 4, 4);
   L.pbc = off;     off += round_up(NS + 2, 4);
   L.mlp = off;     off += kResBufs * T * ld;
-  L.sel = off;     off += round_up(6 * T, 4);  // parent, action, next, depth, reward, value
+  L.sel = off;     off += round_up(7 * T, 4);  // parent, action, next, depth, fresh, reward, value
   L.path = off;    off += round_up(T * PL, 4);
   L.total_floats = round_up(off, 4);
   return L;
-}
-
-// View of the trees starting at global row `row0` (local tree index 0..R-1 inside the CTA).
-__device__ __forceinline__ Tree tree_rows(const Tree& g, int row0, int num_sims) {
-  Tree t = g;
-  const long n0 = (long)row0 * g.N, c0 = n0 * g.A;
-  t.node_visits += n0; t.parents += n0; t.action_from_parent += n0; t.raw_values += n0; t.node_values += n0;
-  t.children_index += c0; t.children_visits += c0; t.children_prior_logits += c0; t.children_prior_probs += c0;
-  t.children_values += c0; t.children_rewards += c0; t.children_discounts += c0;
-  t.embeddings += n0 * g.E;
-  t.root_noise += (long)row0 * g.A;
-  t.root_invalid += (long)row0 * g.A;
-  t.sim_depth += (long)row0 * num_sims;
-  return t;
 }
 
 #ifndef MZ_RES_MIN_CTAS
@@ -410,6 +569,7 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   const int R = min(T, a.t.B - row0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int NS = a.p.num_simulations;
+  const int N = NS + 1;  // record stride: nodes of this search
   const ResidentLayout L = resident_layout(kWSmem ? a.weight_bytes : 0, NS, T, ld, a.PL);
   const int act_kind = a.net.activation;
 
@@ -424,36 +584,24 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
     w = ws;
   }
 
-  const Tree t = tree_rows(a.t, row0, NS);
-  const int N = t.N;
+  RecTrees t;
+  t.N = N; t.A = A; t.E = E; t.embN = a.t.N;
+  t.nodes = a.rec_nodes + (size_t)row0 * N;
+  t.childs = a.rec_childs + (size_t)row0 * N * A * 2;
+  t.emb = a.t.embeddings + (size_t)row0 * a.t.N * E;  // NB: the SoA embeddings keep the handle's node stride
+  t.root_noise = a.t.root_noise + (size_t)row0 * A;
+  t.root_invalid = a.t.root_invalid + (size_t)row0 * A;
+  t.sim_depth = a.t.sim_depth + (size_t)row0 * NS;
 
-  // mctx initial state (Appendix A.1) for this CTA's rows: zeros, parents / action_from_parent / children_index = -1
-  {
-    const int RN = R * N, RNA = RN * A;
-    for (int i = tid; i < RN; i += blockDim.x) {
-      t.node_visits[i] = 0;
-      t.parents[i] = -1;
-      t.action_from_parent[i] = -1;
-      t.raw_values[i] = 0.0f;
-      t.node_values[i] = 0.0f;
-    }
-    for (int i = tid; i < RNA; i += blockDim.x) {
-      t.children_index[i] = -1;
-      t.children_visits[i] = 0;
-      t.children_prior_logits[i] = 0.0f;
-      t.children_prior_probs[i] = 0.0f;
-      t.children_values[i] = 0.0f;
-      t.children_rewards[i] = 0.0f;
-      t.children_discounts[i] = 0.0f;
-    }
-    if (a.clear_embeddings) {
-      const long n = (long)RN * E;
-      if ((E & 3) == 0) {  // row0 * N * E * 4 bytes is a multiple of 16
-        float4* e4 = reinterpret_cast<float4*>(t.embeddings);
-        for (long i = tid; i < n / 4; i += blockDim.x) e4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      } else {
-        for (long i = tid; i < n; i += blockDim.x) t.embeddings[i] = 0.0f;
-      }
+  // node records start as "never expanded" (visits = 0); child records are written when their node is expanded
+  for (int i = tid; i < R * N; i += blockDim.x) t.nodes[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(kRecNoParent));
+  if (a.clear_embeddings) {
+    const long n = (long)R * a.t.N * E;
+    if ((E & 3) == 0) {  // row0 * N * E * 4 bytes is a multiple of 16
+      float4* e4 = reinterpret_cast<float4*>(t.emb);
+      for (long i = tid; i < n / 4; i += blockDim.x) e4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    } else {
+      for (long i = tid; i < n; i += blockDim.x) t.emb[i] = 0.0f;
     }
   }
 
@@ -474,7 +622,8 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   int32_t* sel_action = sel_parent + T;
   int32_t* sel_next = sel_action + T;
   int32_t* sel_depth = sel_next + T;
-  float* rec_reward = reinterpret_cast<float*>(sel_depth + T);
+  int32_t* sel_fresh = sel_depth + T;
+  float* rec_reward = reinterpret_cast<float*>(sel_fresh + T);
   float* rec_value = rec_reward + T;
   uint32_t* path = reinterpret_cast<uint32_t*>(smem + L.path);
 
@@ -521,28 +670,26 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   __syncthreads();
   if (tid < R && a.root_value_out != nullptr) a.root_value_out[row0 + tid] = rec_value[tid];  // raw value (model.py:243)
 
-  // ---- lane groups: group q of warp w owns trees b = (q + i * gpw) * nwarps + w — consecutive trees go to different
-  // warps so that their walks overlap instead of diverging inside one warp
-  constexpr int gpw = 32 / G;
-  const int q = lane / G;        // group inside the warp
-  const int ga = lane & (G - 1); // action handled by this lane
+  // ---- lane groups: group g of the CTA owns trees g, g + ngroups, ...  Trees that share a warp advance level by
+  // level together (same loop body), so packing them costs no latency and divides the instruction count.
+  const int ngroups = blockDim.x / G;
+  const int gi = tid / G;
+  const int ga = tid & (G - 1);  // action handled by this lane
   const unsigned gm = group_mask<G>();
   const bool use_table = a.noise_table != nullptr && a.K > 0 && p.policy == MZ_POLICY_MUZERO;
   const size_t nz_row = (size_t)a.K * A;
 
-  for (int s = q; s * nwarps + warp < R; s += gpw) {
-    const int b = s * nwarps + warp;
+  for (int b = gi; b < R; b += ngroups) {
     const long ba = (long)(row0 + b) * A;
-    group_begin<G>(t, p, b, (long)p.batch_offset + b, headP + b * ld, rec_value[b], ns + b * ld,
-                   a.invalid != nullptr ? a.invalid + ba : nullptr, a.noise != nullptr ? a.noise + ba : nullptr, ga, gm);
+    rec_begin<G>(t, p, b, (long)p.batch_offset + b, headP + b * ld, rec_value[b], ns + b * ld,
+                 a.invalid != nullptr ? a.invalid + ba : nullptr, a.noise != nullptr ? a.noise + ba : nullptr, ga, gm);
   }
   __syncthreads();
 
   // ---- simulations
   for (int sim = 0; sim < NS; ++sim) {
     // A: select
-    for (int s = q; s * nwarps + warp < R; s += gpw) {
-      const int b = s * nwarps + warp;
+    for (int b = gi; b < R; b += ngroups) {
       SelectAux aux;
       aux.noise_row = nullptr;
       aux.K = 0;
@@ -557,20 +704,23 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
         if (sim + 1 < NS && ga == 0) prefetch_l1(aux.noise_row + nz_row);
       }
       int parent, action, next, depth;
-      group_simulate<G>(t, p, b, sim, ga, gm, parent, action, next, depth, &aux, path + b * a.PL);
+      bool fresh;
+      rec_simulate<G>(t, p, b, sim, ga, gm, parent, action, next, depth, fresh, aux, path + b * a.PL);
       if (ga == 0) {
         sel_parent[b] = parent;
         sel_action[b] = action;
         sel_next[b] = next;
         sel_depth[b] = depth;
-        t.sim_depth[(long)b * NS + sim] = depth;
+        sel_fresh[b] = fresh ? 1 : 0;
+        t.sim_depth[(size_t)b * NS + sim] = depth;
       }
-      for (int e = ga; e < E; e += G) x[b * ld + e] = t.embeddings[((long)b * N + parent) * E + e];
+      const float* pe = t.emb + ((size_t)b * t.embN + parent) * E;
+      for (int e = ga; e < E; e += G) x[b * ld + e] = pe[e];
     }
     __syncthreads();
     // B: Dynamic (muax/model.py:269-271): next state -> ns, reward logits -> headR
     run_stacks<kLdg>(a.net.dyn_ns, &a.net.dyn_r, w, act_kind, x, ld, E, sel_action, ns, headR, ld, ta0, ta1, tb0, tb1, ld, R);
-    // C: min-max of the next state + reward support transform, one warp per row (the warp that walks the tree)
+    // C: min-max of the next state + reward support transform, one warp per row
     for (int r = warp; r < R; r += nwarps) {
       if (a.net.dyn_minmax) min_max_row_warp(ns + r * ld, E, lane);
       const float rv = support_to_scalar_warp(headR + r * ld, S, lane);
@@ -580,17 +730,17 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
     // D: Prediction (model.py:272): value logits -> headV, policy logits -> headP
     run_stacks<kLdg>(a.net.pred_v, &a.net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ld, ta0, ta1, tb0, tb1,
                      ld, R);
-    // F: value support transform, then expand + backup by the tree's lane group
+    // E: value support transform, one warp per row
     for (int r = warp; r < R; r += nwarps) {
       const float v = support_to_scalar_warp(headV + r * ld, S, lane);
       if (lane == 0) rec_value[r] = v;
     }
-    __syncwarp();
-    for (int s = q; s * nwarps + warp < R; s += gpw) {
-      const int b = s * nwarps + warp;
+    __syncthreads();
+    // F: expand + backup by the tree's lane group
+    for (int b = gi; b < R; b += ngroups) {
       const float logit = ga < A ? headP[b * ld + ga] : 0.0f;
-      resident_expand_backup<G>(t, b, sel_parent[b], sel_action[b], sel_next[b], rec_reward[b], p.discount, rec_value[b],
-                                logit, ns + b * ld, ga, gm, path + b * a.PL, sel_depth[b]);
+      rec_expand_backup<G>(t, b, sel_parent[b], sel_action[b], sel_next[b], sel_fresh[b] != 0, rec_reward[b], p.discount,
+                           rec_value[b], logit, ns + b * ld, ga, gm, path + b * a.PL, sel_depth[b]);
     }
     // the next select of a tree runs on the lanes of the same group: a warp-level fence orders the backup's global
     // writes before it; the staging buffers are only rewritten after the next CTA barrier
@@ -598,11 +748,10 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   }
 
   // ---- policy epilogue
-  for (int s = q; s * nwarps + warp < R; s += gpw) {
-    const int b = s * nwarps + warp;
+  for (int b = gi; b < R; b += ngroups) {
     int action;
     float weight;
-    group_finish<G>(t, p, b, (long)p.batch_offset + b, a.invalid != nullptr, ga, gm, action, weight);
+    rec_finish<G>(t, p, b, (long)p.batch_offset + b, a.invalid != nullptr, ga, gm, action, weight);
     if (ga < A) a.weights_out[(long)(row0 + b) * A + ga] = weight;
     if (ga == 0) a.action_out[row0 + b] = action;
   }
@@ -668,9 +817,30 @@ int resident_init(ResidentState& st, const Net& net, int device, std::string* er
 void resident_destroy(ResidentState& st) {
   if (st.noise_table) cudaFree(st.noise_table);
   if (st.cont_keys) cudaFree(st.cont_keys);
+  if (st.rec_nodes) cudaFree(st.rec_nodes);
+  if (st.rec_childs) cudaFree(st.rec_childs);
   st.noise_table = nullptr;
   st.cont_keys = nullptr;
-  st.noise_capacity = st.cont_capacity = 0;
+  st.rec_nodes = st.rec_childs = nullptr;
+  st.noise_capacity = st.cont_capacity = st.rec_capacity = 0;
+  st.dirty = false;
+}
+
+// Records of the last search -> the handle's SoA arrays (lazily, when the tree view is asked for).
+int resident_unpack(ResidentState& st, const Tree& tree, float gamma, std::string* err) {
+  if (!st.dirty) return 0;
+  const long n = (long)tree.B * tree.N;
+  resident_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st.last_stream>>>(
+      reinterpret_cast<const float4*>(st.rec_nodes), reinterpret_cast<const float4*>(st.rec_childs), tree,
+      st.last_num_sims + 1, gamma);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st.last_stream);
+  if (e != cudaSuccess) {
+    *err = std::string("resident engine: unpacking the tree records failed: ") + cudaGetErrorString(e);
+    return 1;
+  }
+  st.dirty = false;
+  return 0;
 }
 
 struct ResidentPlan {
@@ -718,7 +888,8 @@ static ResidentPlan resident_plan(const ResidentState& st, const Net& net, int B
 }
 
 bool resident_supported(const ResidentState& st, const Net& net, int B, int num_simulations) {
-  return st.available && resident_plan(st, net, B, num_simulations, 0).T > 0;
+  // child records pack the child index and the visit count into 16 bits each
+  return st.available && num_simulations + 1 < (int)kRecNoChild && resident_plan(st, net, B, num_simulations, 0).T > 0;
 }
 
 int resident_launch(ResidentState& st, const Net& net, const float* weights, const Tree& tree, const SearchParams& p,
@@ -750,6 +921,23 @@ int resident_launch(ResidentState& st, const Net& net, const float* weights, con
   a.ld = round_up(net.max_width, 4);
   a.PL = plan.PL;
   a.clear_embeddings = (p.max_depth > 0 || NS + 1 < tree.N) ? 1 : 0;
+  {
+    const size_t nodes = (size_t)B * (NS + 1);
+    if (nodes > st.rec_capacity) {
+      if (st.rec_nodes) cudaFree(st.rec_nodes);
+      if (st.rec_childs) cudaFree(st.rec_childs);
+      st.rec_nodes = st.rec_childs = nullptr;
+      st.rec_capacity = 0;
+      if (cudaMalloc(&st.rec_nodes, nodes * 16) != cudaSuccess || cudaMalloc(&st.rec_childs, nodes * A * 32) != cudaSuccess) {
+        cudaGetLastError();
+        *err = "resident engine: cudaMalloc(tree records) failed";
+        return 1;
+      }
+      st.rec_capacity = nodes;
+    }
+    a.rec_nodes = reinterpret_cast<float4*>(st.rec_nodes);
+    a.rec_childs = reinterpret_cast<float4*>(st.rec_childs);
+  }
   // tie-break noise ahead of the search (MuZero policy only: the Gumbel selectors ignore their key)
   if (p.policy == MZ_POLICY_MUZERO && NS > 0 && st.noise_levels > 0) {
     const size_t pairs = (size_t)B * NS;
@@ -795,6 +983,9 @@ int resident_launch(ResidentState& st, const Net& net, const float* weights, con
     *err = std::string("resident engine launch failed: ") + cudaGetErrorString(e);
     return 1;
   }
+  st.dirty = true;
+  st.last_stream = stream;
+  st.last_num_sims = NS;
   return 0;
 }
 

@@ -25,6 +25,12 @@ struct ResidentState {
   float* noise_table = nullptr;  // [B][NS][K][A]
   uint32_t* cont_keys = nullptr; // [B][NS][2] carried key after K levels
   size_t noise_capacity = 0, cont_capacity = 0;
+  void* rec_nodes = nullptr;     // [B][NS + 1] 16-byte node records of the last search
+  void* rec_childs = nullptr;    // [B][NS + 1][A][2] 16-byte child records
+  size_t rec_capacity = 0;       // in nodes
+  bool dirty = false;            // the SoA tree view is stale: resident_unpack() refreshes it
+  cudaStream_t last_stream = nullptr;
+  int last_num_sims = 0;
 };
 
 int resident_init(ResidentState& st, const Net& net, int device, std::string* err);
@@ -35,5 +41,8 @@ int resident_launch(ResidentState& st, const Net& net, const float* weights, con
                     const float* obs, const float* root_emb, const float* root_logits, const float* root_value,
                     const uint8_t* invalid, const float* noise, int32_t* action_out, float* weights_out,
                     float* root_value_out, cudaStream_t stream, int64_t* launches, std::string* err);
+
+// Records of the last search -> the handle's SoA arrays (no-op unless a resident search ran since the last call).
+int resident_unpack(ResidentState& st, const Tree& tree, float gamma, std::string* err);
 
 }  // namespace mz

@@ -551,6 +551,7 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
     return fail("root_logits and root_value must be given together");
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   if (stage_keys(h, args, stream)) return 1;
+  h->resident.dirty = false;  // whatever runs next owns the SoA tree view
   MZ_CUDA(cudaEventRecord(h->ev_start, stream));
   int engine = args->engine;
   const bool have_w = obs != nullptr && h->weights != nullptr;
@@ -876,6 +877,7 @@ int mz_begin(mz_handle* h, const float* root_logits_dev, const float* root_value
   if (check_args(h, args)) return 1;
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   if (stage_keys(h, args, (cudaStream_t)stream)) return 1;
+  h->resident.dirty = false;
   return launch_begin(h, root_logits_dev, root_value_dev, root_emb_dev, invalid_dev, noise_dev, (cudaStream_t)stream);
 }
 
@@ -917,6 +919,10 @@ int mz_finish(mz_handle* h, int32_t* action_out_dev, float* action_weights_out_d
 int mz_get_tree(mz_handle* h, mz_tree_view* v) {
   if (h == nullptr || v == nullptr) return mz::fail("mz_get_tree: NULL argument");
   const mz::Tree& t = h->tree;
+  {  // the CTA-resident engine keeps packed records; the mctx SoA view is produced when somebody asks for it
+    std::string err;
+    if (mz::resident_unpack(h->resident, t, h->cfg.discount, &err)) return mz::fail(err);
+  }
   v->batch = t.B;
   v->num_nodes = t.N;
   v->num_actions = t.A;
