@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmzsearch.so")
+LIB_PATH = os.environ.get("MZ_LIB_PATH") or os.path.join(_HERE, "libmzsearch.so")  # MZ_LIB_PATH: A/B builds
 
 MAX_LAYERS = 8
 MAX_ACTIONS = 32
@@ -58,7 +58,7 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    if build_if_missing and not os.environ.get("MZ_LIB_PATH"):
         from .csrc import build as _build
         _build.build()
     if not os.path.exists(LIB_PATH):

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
-OUT = os.path.join(PKG, "libmzsearch.so")
+OUT = os.environ.get("MZ_LIB_OUT") or os.path.join(PKG, "libmzsearch.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
 HEADERS = [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_fused.cuh", "mz_group.cuh", "mz_lane.cuh",
                                             "mz_lane2.cuh", "mz_resident.cuh")] + [

@@ -16,6 +16,7 @@
 #include "mz_resident.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 
@@ -51,94 +52,297 @@ struct DenseJob {    // one hk.Linear applied to R rows staged in shared memory
 };
 
 // Two layers that run in the same phase (the two heads of a module); B.nout == 0 for a single layer.
-// Work item = (tile of RT rows, output unit j); y[r][j] = (sum_k fma(x[r][k], W[k][j])) (+ W[nin + onehot[r]][j]) + b[j]
-// with k ascending — the accumulation order of the CPU checkers.  RT rows share every weight load.
-template <bool kLdg, int RT>
-__device__ __noinline__ void dense_pair(const DenseJob A, const DenseJob B, int R, const int32_t* onehot, int act_kind,
-                                        int apply_act) {
-  const int na = A.nout, ntot = na + B.nout;
+// Work item = (tile of RT rows, quad of 4 output units): y[r][j] = (sum_k fma(x[r][k], W[k][j])) (+ W[nin + onehot[r]][j])
+// + b[j] with k ascending — the accumulation order of the CPU checkers; RT x 4 independent chains per thread.
+// kVec: W rows are 16-byte aligned and nout % 4 == 0 for both layers, so a quad of weights is one 128-bit load;
+// otherwise four scalar loads at consecutive addresses (a partial last quad re-reads the last unit and drops it).
+__device__ __forceinline__ float4 ld_quad_vec(const float* p, bool ldg) {
+  if (ldg) return __ldg(reinterpret_cast<const float4*>(p));
+  return lds_v4(smem_u32(p));
+}
+
+template <bool kLdg, int RT, bool kVec>
+__device__ __noinline__ void dense_quads(const DenseJob A, const DenseJob B, int R, const int32_t* onehot, int act_kind,
+                                         int apply_act) {
+  const int qa = (A.nout + 3) >> 2, qtot = qa + ((B.nout + 3) >> 2);
   const int tiles = (R + RT - 1) / RT;
-  for (int item = threadIdx.x; item < tiles * ntot; item += blockDim.x) {
-    const int tile = item / ntot;
-    int j = item - tile * ntot;
-    const bool second = j >= na;
-    if (second) j -= na;
+  for (int item = threadIdx.x; item < tiles * qtot; item += blockDim.x) {
+    const int tile = item / qtot;
+    int q = item - tile * qtot;
+    const bool second = q >= qa;
+    if (second) q -= qa;
     const DenseJob& J = second ? B : A;
     const int nin = J.nin, nout = J.nout;
+    const int j0 = q * 4;
     const int r0 = tile * RT;
+    // column offsets of the quad (clamped for a partial last quad; only used by the scalar path)
+    const int c1 = min(j0 + 1, nout - 1) - j0, c2 = min(j0 + 2, nout - 1) - j0, c3 = min(j0 + 3, nout - 1) - j0;
     uint32_t xa[RT];
-    float acc[RT];
+    float acc[RT][4];
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
       xa[i] = smem_u32(J.src + min(r0 + i, R - 1) * J.lds);
-      acc[i] = 0.0f;
+      acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
     }
-    const float* Wg = J.W + j;
-    const uint32_t Ws = kLdg ? 0u : smem_u32(Wg);
+    const float* wp = J.W + j0;  // row k of the quad: wp + k * nout
+    auto load_quad = [&](const float* p) -> float4 {
+      if constexpr (kVec) {
+        return ld_quad_vec(p, kLdg);
+      } else if constexpr (kLdg) {
+        return make_float4(__ldg(p), __ldg(p + c1), __ldg(p + c2), __ldg(p + c3));
+      } else {
+        const uint32_t s = smem_u32(p);
+        return make_float4(lds_f32(s), lds_f32(s + 4u * c1), lds_f32(s + 4u * c2), lds_f32(s + 4u * c3));
+      }
+    };
     int k = 0;
 #pragma unroll 1
     for (; k + 4 <= nin; k += 4) {
-      float w0, w1, w2, w3;
-      if constexpr (kLdg) {
-        w0 = __ldg(Wg + (size_t)k * nout);
-        w1 = __ldg(Wg + (size_t)(k + 1) * nout);
-        w2 = __ldg(Wg + (size_t)(k + 2) * nout);
-        w3 = __ldg(Wg + (size_t)(k + 3) * nout);
-      } else {
-        w0 = lds_f32(Ws + (uint32_t)(k * nout) * 4u);
-        w1 = lds_f32(Ws + (uint32_t)((k + 1) * nout) * 4u);
-        w2 = lds_f32(Ws + (uint32_t)((k + 2) * nout) * 4u);
-        w3 = lds_f32(Ws + (uint32_t)((k + 3) * nout) * 4u);
-      }
+      const float4 wa = load_quad(wp);
+      const float4 wb = load_quad(wp + nout);
+      const float4 wc = load_quad(wp + 2 * nout);
+      const float4 wd = load_quad(wp + 3 * nout);
+      wp += 4 * nout;
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
         const float4 xv = lds_v4(xa[i] + (uint32_t)k * 4u);
-        acc[i] = MZ_FMA(xv.x, w0, acc[i]);
-        acc[i] = MZ_FMA(xv.y, w1, acc[i]);
-        acc[i] = MZ_FMA(xv.z, w2, acc[i]);
-        acc[i] = MZ_FMA(xv.w, w3, acc[i]);
+        acc[i][0] = MZ_FMA(xv.x, wa.x, acc[i][0]); acc[i][1] = MZ_FMA(xv.x, wa.y, acc[i][1]);
+        acc[i][2] = MZ_FMA(xv.x, wa.z, acc[i][2]); acc[i][3] = MZ_FMA(xv.x, wa.w, acc[i][3]);
+        acc[i][0] = MZ_FMA(xv.y, wb.x, acc[i][0]); acc[i][1] = MZ_FMA(xv.y, wb.y, acc[i][1]);
+        acc[i][2] = MZ_FMA(xv.y, wb.z, acc[i][2]); acc[i][3] = MZ_FMA(xv.y, wb.w, acc[i][3]);
+        acc[i][0] = MZ_FMA(xv.z, wc.x, acc[i][0]); acc[i][1] = MZ_FMA(xv.z, wc.y, acc[i][1]);
+        acc[i][2] = MZ_FMA(xv.z, wc.z, acc[i][2]); acc[i][3] = MZ_FMA(xv.z, wc.w, acc[i][3]);
+        acc[i][0] = MZ_FMA(xv.w, wd.x, acc[i][0]); acc[i][1] = MZ_FMA(xv.w, wd.y, acc[i][1]);
+        acc[i][2] = MZ_FMA(xv.w, wd.z, acc[i][2]); acc[i][3] = MZ_FMA(xv.w, wd.w, acc[i][3]);
       }
     }
     for (; k < nin; ++k) {
-      const float wk = kLdg ? __ldg(Wg + (size_t)k * nout) : lds_f32(Ws + (uint32_t)(k * nout) * 4u);
+      const float4 wk = load_quad(wp);
+      wp += nout;
 #pragma unroll
-      for (int i = 0; i < RT; ++i) acc[i] = MZ_FMA(lds_f32(xa[i] + (uint32_t)k * 4u), wk, acc[i]);
+      for (int i = 0; i < RT; ++i) {
+        const float xk = lds_f32(xa[i] + (uint32_t)k * 4u);
+        acc[i][0] = MZ_FMA(xk, wk.x, acc[i][0]); acc[i][1] = MZ_FMA(xk, wk.y, acc[i][1]);
+        acc[i][2] = MZ_FMA(xk, wk.z, acc[i][2]); acc[i][3] = MZ_FMA(xk, wk.w, acc[i][3]);
+      }
     }
     if (onehot != nullptr) {  // [x, one_hot(action)] @ W = x @ W[:nin] + W[nin + action]  (muax/nn.py:105-108)
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
-        const int row = nin + onehot[min(r0 + i, R - 1)];
-        const float wo = kLdg ? __ldg(Wg + (size_t)row * nout) : lds_f32(Ws + (uint32_t)(row * nout) * 4u);
-        acc[i] = MZ_ADD(acc[i], wo);
+        const float4 wo = load_quad(wp + (size_t)onehot[min(r0 + i, R - 1)] * nout);  // wp == row nin here
+        acc[i][0] = MZ_ADD(acc[i][0], wo.x); acc[i][1] = MZ_ADD(acc[i][1], wo.y);
+        acc[i][2] = MZ_ADD(acc[i][2], wo.z); acc[i][3] = MZ_ADD(acc[i][3], wo.w);
       }
     }
-    const float bj = kLdg ? __ldg(J.bias + j) : lds_f32(smem_u32(J.bias + j));
-    const uint32_t da = smem_u32(J.dst + j);
+    float4 bq;
+    {
+      const float* bp = J.bias + j0;
+      if constexpr (kLdg) {
+        bq = make_float4(__ldg(bp), __ldg(bp + c1), __ldg(bp + c2), __ldg(bp + c3));
+      } else {
+        const uint32_t s = smem_u32(bp);
+        bq = make_float4(lds_f32(s), lds_f32(s + 4u * c1), lds_f32(s + 4u * c2), lds_f32(s + 4u * c3));
+      }
+    }
+    const int valid = min(4, nout - j0);
+    const uint32_t da = smem_u32(J.dst + j0);
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
       if (r0 + i < R) {
-        float y = MZ_ADD(acc[i], bj);
-        if (apply_act) y = activate(y, act_kind);
-        sts_f32(da + (uint32_t)((r0 + i) * J.ldd) * 4u, y);
+        float y[4] = {MZ_ADD(acc[i][0], bq.x), MZ_ADD(acc[i][1], bq.y), MZ_ADD(acc[i][2], bq.z), MZ_ADD(acc[i][3], bq.w)};
+        const uint32_t d = da + (uint32_t)((r0 + i) * J.ldd) * 4u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < valid) {
+            if (apply_act) y[c] = activate(y[c], act_kind);
+            sts_f32(d + 4u * c, y[c]);
+          }
+        }
       }
     }
   }
 }
 
-// Smallest row tile that covers the layer in one pass of the CTA (more rows per thread = fewer weight loads, fewer
-// threads busy): parallelism first, register tiling only once every thread has work.
+// ------------------------------------------------------------------------------------------ TMA-staged weights
+// Wide nets (C5: 1.4 MB of fp32 weights) do not fit shared memory, and a plain load per k-step leaves every FMA
+// waiting for an L2 round trip (measured: 170k cycles per Dynamic pass).  Here the weight rows of the two heads are
+// streamed through a ring of kTmaStages shared-memory stages by TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx): thread 0 keeps kTmaStages - 1 chunks of kTmaKC rows in flight while all threads run the FMA chains
+// of the current chunk out of shared memory with 128-bit loads.  Accumulation order is unchanged (k ascending).
+constexpr int kTmaKC = 16;     // weight rows per chunk
+constexpr int kTmaStages = 3;
+
+// mbarrier wait that cannot hang the GPU: a chunk that has not landed after ~1 s of polling is a bug -> trap.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 24)) __trap();
+  }
+}
+
+struct TmaRing {
+  float* stage;          // kTmaStages x stage_floats (shared), or null when the ring is disabled
+  uint64_t* full;        // kTmaStages mbarriers: "chunk has landed"
+  int32_t stage_floats;
+  uint32_t g;            // chunks issued so far (stage = g % kTmaStages, parity = (g / kTmaStages) & 1); CTA-uniform
+};
+
+template <int RT, bool kVec>
+__device__ __noinline__ void dense_tma(const DenseJob A, const DenseJob B, int R, const int32_t* onehot, int act_kind,
+                                       int apply_act, TmaRing* ring) {
+  constexpr int KC = kTmaKC, S = kTmaStages;
+  const int na = A.nout, nb = B.nout, nin = A.nin;
+  const int qa = (na + 3) >> 2, qtot = qa + ((nb + 3) >> 2);
+  const int tiles = (R + RT - 1) / RT, total = tiles * qtot;
+  const int nchunks = (nin + KC - 1) / KC;
+  const uint32_t stage0 = smem_u32(ring->stage);
+  for (int pass0 = 0; pass0 < total; pass0 += blockDim.x) {
+    const int item = min(pass0 + (int)threadIdx.x, total - 1);  // a thread without an item recomputes the last one
+    const bool valid = pass0 + (int)threadIdx.x < total;
+    const int tile = item / qtot;
+    int q = item - tile * qtot;
+    const bool second = q >= qa;
+    if (second) q -= qa;
+    const DenseJob& J = second ? B : A;
+    const int nout = J.nout;
+    const int j0 = q * 4;
+    const int r0 = tile * RT;
+    const int c1 = min(j0 + 1, nout - 1) - j0, c2 = min(j0 + 2, nout - 1) - j0, c3 = min(j0 + 3, nout - 1) - j0;
+    const uint32_t col_off = (uint32_t)((second ? KC * na : 0) + j0) * 4u;  // byte offset of the quad inside a stage
+    uint32_t xa[RT];
+    float acc[RT][4];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      xa[i] = smem_u32(J.src + min(r0 + i, R - 1) * J.lds);
+      acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+    }
+    const uint32_t g0 = ring->g;
+    auto issue = [&](int c) {
+      const uint32_t gi = g0 + (uint32_t)c;
+      const int st = (int)(gi % S);
+      const int rows = min(KC, nin - c * KC);
+      float* dst = ring->stage + (size_t)st * ring->stage_floats;
+      mbar_expect_tx(&ring->full[st], (uint32_t)(rows * (na + nb)) * 4u);
+      tma_bulk_g2s(dst, A.W + (size_t)c * KC * na, (uint32_t)(rows * na) * 4u, &ring->full[st]);
+      if (nb > 0) tma_bulk_g2s(dst + KC * na, B.W + (size_t)c * KC * nb, (uint32_t)(rows * nb) * 4u, &ring->full[st]);
+    };
+    if (threadIdx.x == 0)
+      for (int c = 0; c < min(S, nchunks); ++c) issue(c);
+    for (int c = 0; c < nchunks; ++c) {
+      if (c > 0) {
+        __syncthreads();  // every thread is done with chunk c - 1: its stage can be refilled
+        if (threadIdx.x == 0 && c + S - 1 < nchunks) issue(c + S - 1);
+      }
+      const uint32_t gi = g0 + (uint32_t)c;
+      mbar_wait_bounded(&ring->full[gi % S], (gi / S) & 1u);
+      const uint32_t wbase = stage0 + (uint32_t)((gi % S) * ring->stage_floats) * 4u + col_off;
+      const int rows = min(KC, nin - c * KC);
+      const uint32_t row_bytes = (uint32_t)nout * 4u;
+#pragma unroll 1
+      for (int kk = 0; kk < rows; kk += 4) {
+        float4 wq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t wa = wbase + (uint32_t)(kk + u) * row_bytes;
+          if constexpr (kVec) {
+            wq[u] = lds_v4(wa);
+          } else {
+            wq[u] = make_float4(lds_f32(wa), lds_f32(wa + 4u * c1), lds_f32(wa + 4u * c2), lds_f32(wa + 4u * c3));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+          const float4 xv = lds_v4(xa[i] + (uint32_t)(c * KC + kk) * 4u);
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[i][0] = MZ_FMA(xs[u], wq[u].x, acc[i][0]);
+            acc[i][1] = MZ_FMA(xs[u], wq[u].y, acc[i][1]);
+            acc[i][2] = MZ_FMA(xs[u], wq[u].z, acc[i][2]);
+            acc[i][3] = MZ_FMA(xs[u], wq[u].w, acc[i][3]);
+          }
+        }
+      }
+    }
+    ring->g = g0 + (uint32_t)nchunks;
+    const float* wrow = J.W + (size_t)nin * nout + j0;  // one-hot rows follow the nin input rows
+    if (onehot != nullptr) {  // [x, one_hot(action)] @ W = x @ W[:nin] + W[nin + action]  (muax/nn.py:105-108)
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        const float* wo = wrow + (size_t)onehot[min(r0 + i, R - 1)] * nout;
+        acc[i][0] = MZ_ADD(acc[i][0], __ldg(wo)); acc[i][1] = MZ_ADD(acc[i][1], __ldg(wo + c1));
+        acc[i][2] = MZ_ADD(acc[i][2], __ldg(wo + c2)); acc[i][3] = MZ_ADD(acc[i][3], __ldg(wo + c3));
+      }
+    }
+    const float* bp = J.bias + j0;
+    const float4 bq = make_float4(__ldg(bp), __ldg(bp + c1), __ldg(bp + c2), __ldg(bp + c3));
+    const int nvalid = valid ? min(4, nout - j0) : 0;
+    const uint32_t da = smem_u32(J.dst + j0);
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      if (r0 + i < R) {
+        float y[4] = {MZ_ADD(acc[i][0], bq.x), MZ_ADD(acc[i][1], bq.y), MZ_ADD(acc[i][2], bq.z), MZ_ADD(acc[i][3], bq.w)};
+        const uint32_t d = da + (uint32_t)((r0 + i) * J.ldd) * 4u;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          if (cc < nvalid) {
+            if (apply_act) y[cc] = activate(y[cc], act_kind);
+            sts_f32(d + 4u * cc, y[cc]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // the last chunks' stages are free before the next pass / layer issues into them
+  }
+}
+
+// Row tile: as few rows per thread as keeps the layer to one pass of the CTA (parallelism first, register tiling —
+// fewer weight loads — only once every thread has work); weights streamed from L2 always amortise over >= 2 rows.
 template <bool kLdg>
 __device__ __forceinline__ void dense_pair_auto(const DenseJob& A, const DenseJob& B, int R, const int32_t* onehot,
-                                                int act_kind, int apply_act) {
-  const int ntot = A.nout + B.nout;
-  int rt = 1;
-  while (rt < 4 && ((R + rt - 1) / rt) * ntot > (int)blockDim.x) rt <<= 1;  // 4 rows is what 64 registers hold
+                                                int act_kind, int apply_act, TmaRing* ring) {
+  const int qtot = ((A.nout + 3) >> 2) + ((B.nout + 3) >> 2);
+  int rt = (kLdg && R > 1) ? 2 : 1;
+  while (rt < 4 && ((R + rt - 1) / rt) * qtot > (int)blockDim.x) rt <<= 1;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(A.W) | reinterpret_cast<uintptr_t>(B.W)) & 15) == 0;
+  const bool vec = ((A.nout | B.nout) & 3) == 0 && aligned;
+  if constexpr (kLdg) {
+    // stream the weight rows through the TMA ring when the layer is long enough to pay for the pipeline
+    if (ring != nullptr && ring->stage != nullptr && aligned && (A.nin & 3) == 0 && A.nin >= 2 * kTmaKC &&
+        (B.nout == 0 || B.nin == A.nin) && kTmaKC * (A.nout + B.nout) <= ring->stage_floats) {
+      if (R > 4 || rt == 4) {
+        if (vec) dense_tma<4, true>(A, B, R, onehot, act_kind, apply_act, ring);
+        else dense_tma<4, false>(A, B, R, onehot, act_kind, apply_act, ring);
+      } else {
+        if (vec) dense_tma<2, true>(A, B, R, onehot, act_kind, apply_act, ring);
+        else dense_tma<2, false>(A, B, R, onehot, act_kind, apply_act, ring);
+      }
+      return;
+    }
+  }
+#define MZ_DENSE(RT_)                                                                   \
+  do {                                                                                  \
+    if (vec)                                                                            \
+      dense_quads<kLdg, RT_, true>(A, B, R, onehot, act_kind, apply_act);               \
+    else                                                                                \
+      dense_quads<kLdg, RT_, false>(A, B, R, onehot, act_kind, apply_act);              \
+  } while (0)
   if (rt == 1)
-    dense_pair<kLdg, 1>(A, B, R, onehot, act_kind, apply_act);
+    MZ_DENSE(1);
   else if (rt == 2)
-    dense_pair<kLdg, 2>(A, B, R, onehot, act_kind, apply_act);
+    MZ_DENSE(2);
   else
-    dense_pair<kLdg, 4>(A, B, R, onehot, act_kind, apply_act);
+    MZ_DENSE(4);
+#undef MZ_DENSE
 }
 
 __device__ __forceinline__ DenseJob make_job(const mz_stack& s, int l, const float* w, const float* src, int lds,
@@ -160,38 +364,39 @@ __device__ __forceinline__ DenseJob make_job(const mz_stack& s, int l, const flo
 template <bool kLdg>
 __device__ __noinline__ void run_lockstep(const mz_stack& sa, const mz_stack* sb, const float* w, int act_kind,
                                              const float* x, int ldx, int in_x, const int32_t* onehot, float* outa,
-                                             float* outb, int ldo, float* ta0, float* ta1, float* tb0, float* tb1,
-                                             int ldt, int R) {
+                                             float* outb, int ldoa, int ldob, float* ta0, float* ta1, float* tb0,
+                                             float* tb1, int ldt, int R, TmaRing* ring) {
   const float *srca = x, *srcb = x;
   int lds = ldx;
   for (int l = 0; l < sa.n_layers; ++l) {
     const bool last = l == sa.n_layers - 1;
     float* dsta = last ? outa : ((l & 1) ? ta1 : ta0);
     float* dstb = last ? outb : ((l & 1) ? tb1 : tb0);
-    const int ldd = last ? ldo : ldt;
-    const DenseJob A = make_job(sa, l, w, srca, lds, in_x, dsta, ldd);
+    const DenseJob A = make_job(sa, l, w, srca, lds, in_x, dsta, last ? ldoa : ldt);
     DenseJob B = A;
     B.nout = 0;
-    if (sb != nullptr) B = make_job(*sb, l, w, srcb, lds, in_x, dstb, ldd);
-    dense_pair_auto<kLdg>(A, B, R, l == 0 ? onehot : nullptr, act_kind, last ? 0 : 1);
+    if (sb != nullptr) B = make_job(*sb, l, w, srcb, lds, in_x, dstb, last ? ldob : ldt);
+    dense_pair_auto<kLdg>(A, B, R, l == 0 ? onehot : nullptr, act_kind, last ? 0 : 1, ring);
     __syncthreads();
     srca = dsta;
     srcb = dstb;
-    lds = ldd;
+    lds = ldt;
   }
 }
 
 template <bool kLdg>
 __device__ __forceinline__ void run_stacks(const mz_stack& sa, const mz_stack* sb, const float* w, int act_kind,
                                            const float* x, int ldx, int in_x, const int32_t* onehot, float* outa,
-                                           float* outb, int ldo, float* ta0, float* ta1, float* tb0, float* tb1, int ldt,
-                                           int R) {
+                                           float* outb, int ldoa, int ldob, float* ta0, float* ta1, float* tb0,
+                                           float* tb1, int ldt, int R, TmaRing* ring) {
   if (sb != nullptr && sa.n_layers != sb->n_layers) {  // heads of different depth: one after the other
-    run_lockstep<kLdg>(sa, nullptr, w, act_kind, x, ldx, in_x, onehot, outa, nullptr, ldo, ta0, ta1, nullptr, nullptr, ldt, R);
-    run_lockstep<kLdg>(*sb, nullptr, w, act_kind, x, ldx, in_x, onehot, outb, nullptr, ldo, tb0, tb1, nullptr, nullptr, ldt, R);
+    run_lockstep<kLdg>(sa, nullptr, w, act_kind, x, ldx, in_x, onehot, outa, nullptr, ldoa, ldoa, ta0, ta1, nullptr,
+                       nullptr, ldt, R, ring);
+    run_lockstep<kLdg>(*sb, nullptr, w, act_kind, x, ldx, in_x, onehot, outb, nullptr, ldob, ldob, tb0, tb1, nullptr,
+                       nullptr, ldt, R, ring);
     return;
   }
-  run_lockstep<kLdg>(sa, sb, w, act_kind, x, ldx, in_x, onehot, outa, outb, ldo, ta0, ta1, tb0, tb1, ldt, R);
+  run_lockstep<kLdg>(sa, sb, w, act_kind, x, ldx, in_x, onehot, outa, outb, ldoa, ldob, ta0, ta1, tb0, tb1, ldt, R, ring);
 }
 
 // ------------------------------------------------------------------------------------------ per-row warp functions
@@ -274,25 +479,102 @@ __global__ void __launch_bounds__(128) resident_noise_kernel(SearchParams p, int
 
 // ------------------------------------------------------------------------------------------ tree records
 // Working layout of the trees in HBM: 16-byte records, so that one level of `simulate` is one node load plus one
-// (MuZero) or two (Gumbel: + prior logit) 16-byte loads per lane, one level of `backward` two loads and two stores,
-// and every field of a node sits at a constant offset from one address.
-//   node  n        : { visits (int), node_value, raw_value, parent << 8 | action  (0xFFFFFFFF: none) }
-//   child (n, a) h0: { child index << 16 | visits  (index 0xFFFF: unvisited), prior prob, value, reward }
-//   child (n, a) h1: { prior logit, -, -, - }
+// 16-byte load per lane, one level of `backward` two loads and two stores, and every field of a node sits at a
+// constant offset from one address.
+//   node  n     : { visits (int), node_value, raw_value, parent << 8 | action  (0xFFFFFFFF: none) }
+//   child (n, a): { child index << 16 | visits  (index 0xFFFF: unvisited), prior prob, value, reward }
+//   logit (n, a): prior logit (own array: the MuZero selection never reads it, the Gumbel selectors do)
 // children_discounts is not stored: on this path it is the constant gamma for every expanded edge (model.py:275) and
 // an unexpanded edge has reward = value = 0, so reward + gamma * value is the same +0 as mctx's 0 + 0 * 0.
 // The mctx SoA view of the C ABI (mz_get_tree) is produced on demand by resident_unpack_kernel.
+//
+// Cache policy: the records are the only data with reuse (every simulation re-walks the top of its tree), so they
+// carry an L2 evict_last hint; embeddings and the tie-break noise are touched once per simulation and stream
+// (ld.cs / st.cs) so that they do not push the records out of the 126 MB L2.
+//
+// Warp discipline: every lane of a warp runs the same loops (a group without a live tree, or whose walk has ended,
+// is predicated off), so all shuffles use the full mask with width G — no per-group mask convergence checks.
 
 constexpr uint32_t kRecNoChild = 0xFFFFu;
 constexpr uint32_t kRecNoParent = 0xFFFFFFFFu;
+constexpr unsigned kFull = 0xffffffffu;
+
+// MZ_RES_WARP_UNIFORM = 1: all lanes of a warp run the walk loops together and shuffle with the full mask;
+// 0: every lane group runs its own loops and shuffles with its group mask (measured faster on B200: a finished
+// group leaves the loop instead of idling through the deepest walk of its warp).
+#ifndef MZ_RES_WARP_UNIFORM
+#define MZ_RES_WARP_UNIFORM 0
+#endif
+template <int G>
+__device__ __forceinline__ unsigned walk_mask() {
+#if MZ_RES_WARP_UNIFORM
+  return kFull;
+#else
+  return group_mask<G>();
+#endif
+}
+__device__ __forceinline__ bool walk_continues(bool active) {
+#if MZ_RES_WARP_UNIFORM
+  return __any_sync(kFull, active);
+#else
+  return active;
+#endif
+}
+
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+#ifndef MZ_RES_REC_HINT
+#define MZ_RES_REC_HINT 0
+#endif
+#ifndef MZ_RES_STREAM_NOISE
+#define MZ_RES_STREAM_NOISE 0
+#endif
+#ifndef MZ_RES_STREAM_EMB
+#define MZ_RES_STREAM_EMB 0
+#endif
+#if MZ_RES_STREAM_NOISE
+#define MZ_LD_NOISE(p) __ldcs(p)
+#else
+#define MZ_LD_NOISE(p) (*(p))
+#endif
+#if MZ_RES_STREAM_EMB
+#define MZ_LD_EMB(p) __ldcs(p)
+#define MZ_ST_EMB(p, v) __stcs(p, v)
+#else
+#define MZ_LD_EMB(p) (*(p))
+#define MZ_ST_EMB(p, v) (*(p) = (v))
+#endif
+#if !MZ_RES_REC_HINT
+__device__ __forceinline__ float4 rec_ld(const float4* p, uint64_t) { return *p; }
+__device__ __forceinline__ void rec_st(float4* p, const float4& v, uint64_t) { *p = v; }
+#else
+__device__ __forceinline__ float4 rec_ld(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void rec_st(float4* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+#endif
 
 struct RecTrees {    // the records of the trees one CTA owns (local tree index 0..R-1)
   float4* nodes;     // [R][N]
-  float4* childs;    // [R][N][A][2]
-  float* emb;        // [R][N][E]  (the handle's SoA embeddings)
+  float4* childs;    // [R][N][A]
+  float* logits;     // [R][N][A]
+  float* emb;        // [R][embN][E]  (the handle's SoA embeddings)
   float* root_noise; // [R][A]
   uint8_t* root_invalid;
   int32_t* sim_depth; // [R][NS]
+  uint64_t pol;       // L2 evict_last access policy for the records
   int32_t N, A, E;    // N = record stride (nodes of this search)
   int32_t embN;       // node stride of the embeddings (the handle's capacity)
 };
@@ -308,32 +590,35 @@ __device__ __forceinline__ ChildRow rec_child_row(const float4& h0, float logit,
   return c;
 }
 
-// Policy prologue (A.2 / A.4) + instantiate_tree_from_root (A.3) for one tree.
+// Policy prologue (A.2 / A.4) + instantiate_tree_from_root (A.3) for one tree.  `has`: this group owns tree b
+// (groups without a tree run the arithmetic on a clamped row and store nothing).
 template <int G>
-__device__ __forceinline__ void rec_begin(const RecTrees& t, const SearchParams& p, int b, long gb,
+__device__ __forceinline__ void rec_begin(const RecTrees& t, const SearchParams& p, int b, bool has, long gb,
                                           const float* root_logits, float root_value, const float* root_emb,
-                                          const uint8_t* invalid, const float* noise, int a, unsigned m) {
+                                          const uint8_t* invalid, const float* noise, int a) {
   const int A = t.A;
   float logit, prob, nz;
   bool inv;
-  group_begin_compute<G>(p, A, gb, root_logits, invalid, noise, a, m, logit, prob, nz, inv);
-  float4* ch = t.childs + (size_t)b * t.N * A * 2;
+  group_begin_compute<G>(p, A, gb, root_logits, invalid, noise, a, walk_mask<G>(), logit, prob, nz, inv);
+  if (!has) return;
   if (a < A) {
-    ch[a * 2] = make_float4(__uint_as_float(kRecNoChild << 16), prob, 0.0f, 0.0f);
-    ch[a * 2 + 1] = make_float4(logit, 0.0f, 0.0f, 0.0f);
+    rec_st(t.childs + (size_t)b * t.N * A + a, make_float4(__uint_as_float(kRecNoChild << 16), prob, 0.0f, 0.0f), t.pol);
+    t.logits[(size_t)b * t.N * A + a] = logit;
     t.root_noise[b * A + a] = nz;
     t.root_invalid[b * A + a] = inv ? 1 : 0;
   }
   float* emb = t.emb + (size_t)b * t.embN * t.E;
-  for (int e = a; e < t.E; e += G) emb[e] = root_emb[e];
+  for (int e = a; e < t.E; e += G) MZ_ST_EMB(emb + e, root_emb[e]);
   if (a == 0)
-    t.nodes[(size_t)b * t.N] = make_float4(__int_as_float(1), root_value, root_value, __uint_as_float(kRecNoParent));
+    rec_st(t.nodes + (size_t)b * t.N, make_float4(__int_as_float(1), root_value, root_value, __uint_as_float(kRecNoParent)),
+           t.pol);
 }
 
-// `simulate` (A.3) for one tree.  `fresh`: the selected edge was unvisited (the new node gets index sim + 1).
+// `simulate` (A.3) for one tree per lane group; all lanes of the warp stay in the level loop until every group of
+// the warp has reached its leaf.  `fresh`: the selected edge was unvisited (the new node gets index sim + 1).
 template <int G>
-__device__ __forceinline__ void rec_simulate(const RecTrees& t, const SearchParams& p, int b, int sim, int a, unsigned m,
-                                             int& parent, int& action, int& next, int& depth_out, bool& fresh,
+__device__ __forceinline__ void rec_simulate(const RecTrees& t, const SearchParams& p, int b, bool has, int sim, int a,
+                                             int& parent, int& action_out, int& next, int& depth_out, bool& fresh,
                                              const SelectAux& aux, uint32_t* path) {
   const int A = t.A;
   const bool ok = a < A;
@@ -345,82 +630,95 @@ __device__ __forceinline__ void rec_simulate(const RecTrees& t, const SearchPara
               p.prng_mode, k0, k1);
   const int max_depth = p.max_depth > 0 ? p.max_depth : p.num_simulations;
   const float4* nodes = t.nodes + (size_t)b * t.N;
-  const float4* ch = t.childs + (size_t)b * t.N * A * 2;
-  const bool root_inv = ok && t.root_invalid[b * A + a] != 0;
-  const float root_gumbel = (!muzero && ok) ? t.root_noise[b * A + a] : 0.0f;
-  int node = 0, depth = 0;
-  uint32_t ci;
-  for (;;) {
-    const float4 nd = nodes[node];
-    float4 h0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  const float4* ch = t.childs + (size_t)b * t.N * A;
+  const float* lg = t.logits + (size_t)b * t.N * A;
+  const bool root_inv = has && ok && t.root_invalid[b * A + a] != 0;
+  const float root_gumbel = (has && !muzero && ok) ? t.root_noise[b * A + a] : 0.0f;
+  int node = 0;
+  bool active = has;
+  parent = 0; action_out = 0; next = 0; depth_out = 0; fresh = false;
+  // `level` is warp-uniform: every group still walking is at the same depth, so the branches on it (root vs interior
+  // selectors, table vs inline noise) never split a warp around a shuffle
+  const unsigned wm = walk_mask<G>();
+  for (int level = 0; walk_continues(active); ++level) {
+    float4 nd = make_float4(0.0f, 0.0f, 0.0f, 0.0f), h0 = nd;
     float logit = 0.0f;
-    if (ok) {
-      h0 = ch[(node * A + a) * 2];
-      if (!muzero) logit = ch[(node * A + a) * 2 + 1].x;
+    if (active) {
+      nd = rec_ld(nodes + node, t.pol);
+      if (ok) {
+        h0 = rec_ld(ch + node * A + a, t.pol);
+        if (!muzero) logit = lg[node * A + a];
+      }
     }
     uint32_t s0 = 0, s1 = 0;
     bool have_noise = false;
     float nz = 0.0f;
     if (muzero) {
-      if (table && depth < aux.K) {
+      if (table && level < aux.K) {
         have_noise = true;
-        nz = aux.noise_row[depth * A + (ok ? a : 0)];
-      } else {
-        if (table && depth == aux.K) {
+        if (active) nz = MZ_LD_NOISE(aux.noise_row + level * A + (ok ? a : 0));
+      } else {  // past the table (or no table): continue the jax key chain inline
+        if (table && level == aux.K) {
           k0 = aux.cont0;
           k1 = aux.cont1;
         }
-        group_split2<G>(k0, k1, p.prng_mode, a, m, k0, k1, s0, s1);
+        group_split2<G>(k0, k1, p.prng_mode, a, wm, k0, k1, s0, s1);
       }
     }
-    const ChildRow c = rec_child_row(h0, logit, p.discount, ok);
-    action = group_select_score<G>(p, A, c, ok, nd.y, nd.z, __float_as_int(nd.x), depth, root_inv, root_gumbel, s0, s1, a,
-                                   m, have_noise, nz, aux.pbc);
-    ci = __shfl_sync(m, __float_as_uint(h0.x) >> 16, action, G);
-    if (a == 0) path[depth] = ((uint32_t)node << 8) | (uint32_t)action;
-    ++depth;
-    if (ci == kRecNoChild || depth >= max_depth) break;
-    node = (int)ci;
+    const ChildRow c = rec_child_row(h0, logit, p.discount, ok && active);
+    const int action = group_select_score<G>(p, A, c, ok, nd.y, nd.z, __float_as_int(nd.x), level, root_inv, root_gumbel,
+                                             s0, s1, a, wm, have_noise, nz, aux.pbc);
+    const uint32_t ci = __shfl_sync(wm, __float_as_uint(h0.x) >> 16, action, G);
+    if (active) {
+      if (a == 0) path[level] = ((uint32_t)node << 8) | (uint32_t)action;
+      if (ci == kRecNoChild || level + 1 >= max_depth) {
+        active = false;
+        parent = node;
+        action_out = action;
+        depth_out = level + 1;
+        fresh = ci == kRecNoChild;
+        next = fresh ? sim + 1 : (int)ci;
+      } else {
+        node = (int)ci;
+      }
+    }
   }
-  parent = node;
-  depth_out = depth;
-  fresh = ci == kRecNoChild;
-  next = fresh ? sim + 1 : (int)ci;
 }
 
 // `expand` scatter (A.3) + `backward` for one tree, walking the path recorded by the selection: the records of
 // level d-1 are loaded while level d's mean update is computed.
 template <int G>
-__device__ __forceinline__ void rec_expand_backup(const RecTrees& t, int b, int parent, int action, int next, bool fresh,
-                                                  float reward, float gamma, float value, float logit_a,
-                                                  const float* next_emb, int a, unsigned m, const uint32_t* path,
-                                                  int depth) {
+__device__ __forceinline__ void rec_expand_backup(const RecTrees& t, int b, bool has, int parent, int action, int next,
+                                                  bool fresh, float reward, float gamma, float value, float logit_a,
+                                                  const float* next_emb, int a, const uint32_t* path, int depth) {
   const int A = t.A;
   const bool ok = a < A;
   float4* nodes = t.nodes + (size_t)b * t.N;
-  float4* ch = t.childs + (size_t)b * t.N * A * 2;
-  const float prob = group_softmax<G>(logit_a, ok, A, m);
+  float4* ch = t.childs + (size_t)b * t.N * A;
+  const float prob = group_softmax<G>(logit_a, ok, A, walk_mask<G>());
+  if (!has) return;
   if (ok) {
     float4 h0 = make_float4(__uint_as_float(kRecNoChild << 16), prob, 0.0f, 0.0f);
     if (!fresh) {  // max_depth re-expansion: priors are overwritten, the edge statistics stay (update_tree_node)
-      h0 = ch[(next * A + a) * 2];
+      h0 = rec_ld(ch + next * A + a, t.pol);
       h0.y = prob;
     }
-    ch[(next * A + a) * 2] = h0;
-    ch[(next * A + a) * 2 + 1] = make_float4(logit_a, 0.0f, 0.0f, 0.0f);
+    rec_st(ch + next * A + a, h0, t.pol);
+    t.logits[((size_t)b * t.N + next) * A + a] = logit_a;
   }
   float* emb = t.emb + ((size_t)b * t.embN + next) * t.E;
-  for (int e = a; e < t.E; e += G) emb[e] = next_emb[e];
+  for (int e = a; e < t.E; e += G) MZ_ST_EMB(emb + e, next_emb[e]);
   if (a == 0) {
-    const int old_visits = fresh ? 0 : __float_as_int(nodes[next].x);
-    nodes[next] = make_float4(__int_as_float(old_visits + 1), value, value,
-                              __uint_as_float(((uint32_t)parent << 8) | (uint32_t)action));
+    const int old_visits = fresh ? 0 : __float_as_int(rec_ld(nodes + next, t.pol).x);
+    rec_st(nodes + next,
+           make_float4(__int_as_float(old_visits + 1), value, value, __uint_as_float(((uint32_t)parent << 8) | (uint32_t)action)),
+           t.pol);
     // backward: path[d] = (node << 8 | action) of the edge selected at depth d; path[depth - 1] = (parent, action)
     float G_ = value, child_value = value;
     int d = depth - 1;
-    int pn = parent, e2 = (parent * A + action) * 2;
-    float4 nd = nodes[pn];
-    float4 c = ch[e2];
+    int pn = parent, e2 = parent * A + action;
+    float4 nd = rec_ld(nodes + pn, t.pol);
+    float4 c = rec_ld(ch + e2, t.pol);
     c.x = __uint_as_float(((uint32_t)next << 16) | (__float_as_uint(c.x) & 0xFFFFu));  // children_index[parent, action]
     c.w = reward;                                                                      // children_rewards[parent, action]
     for (;;) {
@@ -429,18 +727,18 @@ __device__ __forceinline__ void rec_expand_backup(const RecTrees& t, int b, int 
       if (d > 0) {
         const uint32_t pa = path[d - 1];
         n_pn = (int)(pa >> 8);
-        n_e2 = (n_pn * A + (int)(pa & 0xffu)) * 2;
-        n_nd = nodes[n_pn];
-        n_c = ch[n_e2];
+        n_e2 = n_pn * A + (int)(pa & 0xffu);
+        n_nd = rec_ld(nodes + n_pn, t.pol);
+        n_c = rec_ld(ch + n_e2, t.pol);
       }
       const int count_i = __float_as_int(nd.x);
       const float count = (float)count_i;
       G_ = MZ_ADD(c.w, MZ_MUL(gamma, G_));
       const float pv = MZ_DIV(MZ_ADD(MZ_MUL(nd.y, count), G_), MZ_ADD(count, 1.0f));
-      nodes[pn] = make_float4(__int_as_float(count_i + 1), pv, nd.z, nd.w);
+      rec_st(nodes + pn, make_float4(__int_as_float(count_i + 1), pv, nd.z, nd.w), t.pol);
       c.x = __uint_as_float(__float_as_uint(c.x) + 1u);  // children_visits += 1 (low 16 bits)
       c.z = child_value;
-      ch[e2] = c;
+      rec_st(ch + e2, c, t.pol);
       child_value = pv;
       if (d == 0) break;
       --d;
@@ -451,29 +749,35 @@ __device__ __forceinline__ void rec_expand_backup(const RecTrees& t, int b, int 
 
 // Policy epilogue for one tree (A.2 / A.4).
 template <int G>
-__device__ __forceinline__ void rec_finish(const RecTrees& t, const SearchParams& p, int b, long gb, bool has_invalid,
-                                           int a, unsigned m, int& action, float& weight) {
+__device__ __forceinline__ void rec_finish(const RecTrees& t, const SearchParams& p, int b, bool has, long gb,
+                                           bool has_invalid, int a, int& action, float& weight) {
   const int A = t.A;
   const bool ok = a < A;
   const bool muzero = p.policy == MZ_POLICY_MUZERO;
-  const float4* ch = t.childs + (size_t)b * t.N * A * 2;
-  const float4 nd = t.nodes[(size_t)b * t.N];
-  float4 h0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  float4 nd = make_float4(0.0f, 0.0f, 0.0f, 0.0f), h0 = nd;
   float logit = 0.0f;
-  if (ok) {
-    h0 = ch[a * 2];
-    if (!muzero) logit = ch[a * 2 + 1].x;
+  bool root_inv = false;
+  float root_gumbel = 0.0f;
+  if (has) {
+    nd = rec_ld(t.nodes + (size_t)b * t.N, t.pol);
+    if (ok) {
+      h0 = rec_ld(t.childs + (size_t)b * t.N * A + a, t.pol);
+      if (!muzero) {
+        logit = t.logits[(size_t)b * t.N * A + a];
+        root_inv = t.root_invalid[b * A + a] != 0;
+        root_gumbel = t.root_noise[b * A + a];
+      }
+    }
   }
-  const ChildRow c = rec_child_row(h0, logit, p.discount, ok);
-  const bool root_inv = !muzero && ok && t.root_invalid[b * A + a] != 0;
-  const float root_gumbel = (!muzero && ok) ? t.root_noise[b * A + a] : 0.0f;
-  group_finish_score<G>(p, A, c, ok, nd.y, nd.z, root_inv, root_gumbel, gb, has_invalid, a, m, action, weight);
+  const ChildRow c = rec_child_row(h0, logit, p.discount, ok && has);
+  group_finish_score<G>(p, A, c, ok, nd.y, nd.z, root_inv, root_gumbel, gb, has_invalid, a, walk_mask<G>(), action, weight);
 }
 
 // Records -> the mctx SoA arrays of the handle (mz_get_tree view).  One thread per (tree, node); nodes that were
 // never expanded (visits == 0) read as mctx's initial state (A.1).
 __global__ void __launch_bounds__(256) resident_unpack_kernel(const float4* __restrict__ nodes,
-                                                             const float4* __restrict__ childs, Tree o, int N_used,
+                                                             const float4* __restrict__ childs,
+                                                             const float* __restrict__ logits, Tree o, int N_used,
                                                              float gamma) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)o.B * o.N) return;
@@ -494,8 +798,8 @@ __global__ void __launch_bounds__(256) resident_unpack_kernel(const float4* __re
     float4 h0 = make_float4(__uint_as_float(kRecNoChild << 16), 0.0f, 0.0f, 0.0f);
     float logit = 0.0f;
     if (visits > 0) {
-      h0 = childs[(rec * A + x) * 2];
-      logit = childs[(rec * A + x) * 2 + 1].x;
+      h0 = childs[rec * A + x];
+      logit = logits[rec * A + x];
     }
     const uint32_t cx = __float_as_uint(h0.x);
     const bool has = (cx >> 16) != kRecNoChild;
@@ -517,7 +821,8 @@ struct ResidentArgs {
   int32_t weight_bytes;  // multiple of 16
   Tree t;                // the handle's SoA tree (embeddings, root_noise, root_invalid, sim_depth are used in place)
   float4* rec_nodes;     // [B][N]
-  float4* rec_childs;    // [B][N][A][2]
+  float4* rec_childs;    // [B][N][A]
+  float* rec_logits;     // [B][N][A]
   SearchParams p;
   const float* obs;          // [B,obs_dim] or null
   const float* root_emb;     // [B,E] when obs is null
@@ -533,30 +838,33 @@ struct ResidentArgs {
   float* root_value_out;
   int32_t T;   // trees per CTA
   int32_t ld;  // MLP staging row stride (floats, multiple of 4)
+  int32_t ldh; // row stride of the head outputs (value / policy / reward logits)
   int32_t PL;  // path slots per tree
+  uint32_t* path;  // [B][PL] selected edges of the current simulation (global scratch, L1 resident)
+  int32_t ring_stage_floats;  // floats per stage of the TMA weight ring (0: no ring)
   int32_t clear_embeddings;
 };
 
 struct ResidentLayout {  // offsets in floats from the dynamic smem base
-  int weights, pbc, mlp, sel, path, total_floats;
+  int weights, pbc, mlp, sel, ring, total_floats;
 };
 
-constexpr int kResBufs = 9;  // x, ns, headV, headP, headR, tmp0A, tmp1A, tmp0B, tmp1B
-
-__host__ __device__ inline ResidentLayout resident_layout(int weight_bytes_in_smem, int NS, int T, int ld, int PL) {
+// staging per tree: x, ns, tmp0A, tmp1A, tmp0B, tmp1B (row stride ld) + headV, headP, headR (row stride ldh)
+__host__ __device__ inline ResidentLayout resident_layout(int weight_bytes_in_smem, int NS, int T, int ld, int ldh,
+                                                         int ring_stage_floats) {
   ResidentLayout L;
   int off = 0;
   L.weights = off; off += round_up(weight_bytes_in_smem / 4, 4);
   L.pbc = off;     off += round_up(NS + 2, 4);
-  L.mlp = off;     off += kResBufs * T * ld;
+  L.mlp = off;     off += T * (6 * ld + 3 * ldh);
   L.sel = off;     off += round_up(7 * T, 4);  // parent, action, next, depth, fresh, reward, value
-  L.path = off;    off += round_up(T * PL, 4);
+  L.ring = off;    off += kTmaStages * ring_stage_floats;  // TMA weight ring (weights not resident in smem)
   L.total_floats = round_up(off, 4);
   return L;
 }
 
 #ifndef MZ_RES_MIN_CTAS
-#define MZ_RES_MIN_CTAS 4  // 64 registers per thread: four 256-thread CTAs per SM
+#define MZ_RES_MIN_CTAS 3  // 80 registers per thread, three 256-thread CTAs per SM (measured: 1-4% faster than 4 x 64)
 #endif
 
 template <int G, bool kWSmem>
@@ -570,7 +878,16 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int NS = a.p.num_simulations;
   const int N = NS + 1;  // record stride: nodes of this search
-  const ResidentLayout L = resident_layout(kWSmem ? a.weight_bytes : 0, NS, T, ld, a.PL);
+  const int ldh = a.ldh;
+  const ResidentLayout L = resident_layout(kWSmem ? a.weight_bytes : 0, NS, T, ld, ldh, kWSmem ? 0 : a.ring_stage_floats);
+  __shared__ __align__(8) uint64_t ring_full[kTmaStages];
+  TmaRing ring;
+  ring.stage = (!kWSmem && a.ring_stage_floats > 0) ? smem + L.ring : nullptr;
+  ring.full = ring_full;
+  ring.stage_floats = a.ring_stage_floats;
+  ring.g = 0;
+  if (!kWSmem && threadIdx.x == 0)
+    for (int i = 0; i < kTmaStages; ++i) mbar_init(&ring_full[i], 1);
   const int act_kind = a.net.activation;
 
   const float* w = a.weights;
@@ -587,7 +904,9 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   RecTrees t;
   t.N = N; t.A = A; t.E = E; t.embN = a.t.N;
   t.nodes = a.rec_nodes + (size_t)row0 * N;
-  t.childs = a.rec_childs + (size_t)row0 * N * A * 2;
+  t.childs = a.rec_childs + (size_t)row0 * N * A;
+  t.logits = a.rec_logits + (size_t)row0 * N * A;
+  t.pol = l2_evict_last_policy();
   t.emb = a.t.embeddings + (size_t)row0 * a.t.N * E;  // NB: the SoA embeddings keep the handle's node stride
   t.root_noise = a.t.root_noise + (size_t)row0 * A;
   t.root_invalid = a.t.root_invalid + (size_t)row0 * A;
@@ -611,13 +930,13 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
 
   float* x = smem + L.mlp;
   float* ns = x + T * ld;
-  float* headV = ns + T * ld;
-  float* headP = headV + T * ld;
-  float* headR = headP + T * ld;
-  float* ta0 = headR + T * ld;
+  float* ta0 = ns + T * ld;
   float* ta1 = ta0 + T * ld;
   float* tb0 = ta1 + T * ld;
   float* tb1 = tb0 + T * ld;
+  float* headV = tb1 + T * ld;
+  float* headP = headV + T * ldh;
+  float* headR = headP + T * ldh;
   int32_t* sel_parent = reinterpret_cast<int32_t*>(smem + L.sel);
   int32_t* sel_action = sel_parent + T;
   int32_t* sel_next = sel_action + T;
@@ -625,7 +944,7 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   int32_t* sel_fresh = sel_depth + T;
   float* rec_reward = reinterpret_cast<float*>(sel_fresh + T);
   float* rec_value = rec_reward + T;
-  uint32_t* path = reinterpret_cast<uint32_t*>(smem + L.path);
+  uint32_t* path = a.path + (size_t)row0 * a.PL;
 
   SearchParams p = a.p;
   p.batch_offset += row0;  // PRNG draws are indexed by global row
@@ -646,24 +965,24 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   if constexpr (kWSmem) mbar_wait(&wbar, 0);
   __syncthreads();
   if (a.obs != nullptr) {
-    run_stacks<kLdg>(a.net.repr, nullptr, w, act_kind, x, ld, obs_dim, nullptr, ns, nullptr, ld, ta0, ta1, nullptr, nullptr,
-                     ld, R);
+    run_stacks<kLdg>(a.net.repr, nullptr, w, act_kind, x, ld, obs_dim, nullptr, ns, nullptr, ld, ld, ta0, ta1, nullptr,
+                     nullptr, ld, R, &ring);
     if (a.net.repr_minmax) {
       for (int r = warp; r < R; r += nwarps) min_max_row_warp(ns + r * ld, E, lane);
       __syncthreads();
     }
   }
   if (a.obs != nullptr || a.root_logits == nullptr) {
-    run_stacks<kLdg>(a.net.pred_v, &a.net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ld, ta0, ta1, tb0, tb1,
-                     ld, R);
+    run_stacks<kLdg>(a.net.pred_v, &a.net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ldh, ldh, ta0, ta1, tb0,
+                     tb1, ld, R, &ring);
     for (int r = warp; r < R; r += nwarps) {
-      const float v = support_to_scalar_warp(headV + r * ld, S, lane);
+      const float v = support_to_scalar_warp(headV + r * ldh, S, lane);
       if (lane == 0) rec_value[r] = v;
     }
   } else {
     for (int i = tid; i < R * A; i += blockDim.x) {
       const int r = i / A, k = i - r * A;
-      headP[r * ld + k] = a.root_logits[(long)(row0 + r) * A + k];
+      headP[r * ldh + k] = a.root_logits[(long)(row0 + r) * A + k];
     }
     if (tid < R) rec_value[tid] = a.root_value[row0 + tid];
   }
@@ -671,25 +990,39 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   if (tid < R && a.root_value_out != nullptr) a.root_value_out[row0 + tid] = rec_value[tid];  // raw value (model.py:243)
 
   // ---- lane groups: group g of the CTA owns trees g, g + ngroups, ...  Trees that share a warp advance level by
-  // level together (same loop body), so packing them costs no latency and divides the instruction count.
-  const int ngroups = blockDim.x / G;
-  const int gi = tid / G;
-  const int ga = tid & (G - 1);  // action handled by this lane
-  const unsigned gm = group_mask<G>();
+  // level together (same loop body), so packing them costs no latency and divides the instruction count.  The tree
+  // loops are warp-uniform (`base`), a group without a live tree is predicated off (`has`).
+  constexpr int gpw = 32 / G;
+  const int ngroups = nwarps * gpw;
+  const int gq = lane / G;       // group inside the warp
+  const int ga = lane & (G - 1); // action handled by this lane
   const bool use_table = a.noise_table != nullptr && a.K > 0 && p.policy == MZ_POLICY_MUZERO;
   const size_t nz_row = (size_t)a.K * A;
 
-  for (int b = gi; b < R; b += ngroups) {
+  for (int base = warp * gpw; base < R; base += ngroups) {
+    const bool has = base + gq < R;
+    const int b = min(base + gq, R - 1);
     const long ba = (long)(row0 + b) * A;
-    rec_begin<G>(t, p, b, (long)p.batch_offset + b, headP + b * ld, rec_value[b], ns + b * ld,
-                 a.invalid != nullptr ? a.invalid + ba : nullptr, a.noise != nullptr ? a.noise + ba : nullptr, ga, gm);
+    if (MZ_RES_WARP_UNIFORM || has)
+      rec_begin<G>(t, p, b, has, (long)p.batch_offset + b, headP + b * ldh, rec_value[b], ns + b * ld,
+                   a.invalid != nullptr ? a.invalid + ba : nullptr, a.noise != nullptr ? a.noise + ba : nullptr, ga);
   }
   __syncthreads();
 
+#ifdef MZ_PHASE_CLOCKS
+  long long phase_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long phase_t = clock64();
+  long long levels = 0;
+#define MZ_RCLK(i) do { const long long t__ = clock64(); phase_acc[i] += t__ - phase_t; phase_t = t__; } while (0)
+#else
+#define MZ_RCLK(i) do { } while (0)
+#endif
   // ---- simulations
   for (int sim = 0; sim < NS; ++sim) {
     // A: select
-    for (int b = gi; b < R; b += ngroups) {
+    for (int base = warp * gpw; base < R; base += ngroups) {
+      const bool has = base + gq < R;
+      const int b = min(base + gq, R - 1);
       SelectAux aux;
       aux.noise_row = nullptr;
       aux.K = 0;
@@ -701,12 +1034,12 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
         aux.K = a.K;
         aux.cont0 = a.cont_keys[2 * pair];
         aux.cont1 = a.cont_keys[2 * pair + 1];
-        if (sim + 1 < NS && ga == 0) prefetch_l1(aux.noise_row + nz_row);
       }
-      int parent, action, next, depth;
-      bool fresh;
-      rec_simulate<G>(t, p, b, sim, ga, gm, parent, action, next, depth, fresh, aux, path + b * a.PL);
-      if (ga == 0) {
+      int parent = 0, action = 0, next = 0, depth = 0;
+      bool fresh = false;
+      if (MZ_RES_WARP_UNIFORM || has)
+        rec_simulate<G>(t, p, b, has, sim, ga, parent, action, next, depth, fresh, aux, path + b * a.PL);
+      if (has && ga == 0) {
         sel_parent[b] = parent;
         sel_action[b] = action;
         sel_next[b] = next;
@@ -714,46 +1047,71 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
         sel_fresh[b] = fresh ? 1 : 0;
         t.sim_depth[(size_t)b * NS + sim] = depth;
       }
-      const float* pe = t.emb + ((size_t)b * t.embN + parent) * E;
-      for (int e = ga; e < E; e += G) x[b * ld + e] = pe[e];
+      if (has) {
+        const float* pe = t.emb + ((size_t)b * t.embN + parent) * E;
+        for (int e = ga; e < E; e += G) x[b * ld + e] = MZ_LD_EMB(pe + e);
+      }
+#ifdef MZ_PHASE_CLOCKS
+      levels += depth;
+#endif
     }
+    MZ_RCLK(0);
     __syncthreads();
+    MZ_RCLK(1);
     // B: Dynamic (muax/model.py:269-271): next state -> ns, reward logits -> headR
-    run_stacks<kLdg>(a.net.dyn_ns, &a.net.dyn_r, w, act_kind, x, ld, E, sel_action, ns, headR, ld, ta0, ta1, tb0, tb1, ld, R);
+    run_stacks<kLdg>(a.net.dyn_ns, &a.net.dyn_r, w, act_kind, x, ld, E, sel_action, ns, headR, ld, ldh, ta0, ta1, tb0, tb1,
+                     ld, R, &ring);
+    MZ_RCLK(2);
     // C: min-max of the next state + reward support transform, one warp per row
     for (int r = warp; r < R; r += nwarps) {
       if (a.net.dyn_minmax) min_max_row_warp(ns + r * ld, E, lane);
-      const float rv = support_to_scalar_warp(headR + r * ld, S, lane);
+      const float rv = support_to_scalar_warp(headR + r * ldh, S, lane);
       if (lane == 0) rec_reward[r] = rv;
     }
     __syncthreads();
+    MZ_RCLK(3);
     // D: Prediction (model.py:272): value logits -> headV, policy logits -> headP
-    run_stacks<kLdg>(a.net.pred_v, &a.net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ld, ta0, ta1, tb0, tb1,
-                     ld, R);
+    run_stacks<kLdg>(a.net.pred_v, &a.net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ldh, ldh, ta0, ta1, tb0,
+                     tb1, ld, R, &ring);
+    MZ_RCLK(4);
     // E: value support transform, one warp per row
     for (int r = warp; r < R; r += nwarps) {
-      const float v = support_to_scalar_warp(headV + r * ld, S, lane);
+      const float v = support_to_scalar_warp(headV + r * ldh, S, lane);
       if (lane == 0) rec_value[r] = v;
     }
     __syncthreads();
+    MZ_RCLK(5);
     // F: expand + backup by the tree's lane group
-    for (int b = gi; b < R; b += ngroups) {
-      const float logit = ga < A ? headP[b * ld + ga] : 0.0f;
-      rec_expand_backup<G>(t, b, sel_parent[b], sel_action[b], sel_next[b], sel_fresh[b] != 0, rec_reward[b], p.discount,
-                           rec_value[b], logit, ns + b * ld, ga, gm, path + b * a.PL, sel_depth[b]);
+    for (int base = warp * gpw; base < R; base += ngroups) {
+      const bool has = base + gq < R;
+      const int b = min(base + gq, R - 1);
+      const float logit = ga < A ? headP[b * ldh + ga] : 0.0f;
+      if (MZ_RES_WARP_UNIFORM || has)
+        rec_expand_backup<G>(t, b, has, sel_parent[b], sel_action[b], sel_next[b], sel_fresh[b] != 0, rec_reward[b],
+                             p.discount, rec_value[b], logit, ns + b * ld, ga, path + b * a.PL, sel_depth[b]);
     }
     // the next select of a tree runs on the lanes of the same group: a warp-level fence orders the backup's global
     // writes before it; the staging buffers are only rewritten after the next CTA barrier
     __syncwarp();
+    MZ_RCLK(6);
   }
+#ifdef MZ_PHASE_CLOCKS
+  if ((blockIdx.x == 1 || blockIdx.x == 100) && lane == 0 && (warp == 0 || warp == 1 || warp == nwarps - 1))
+    printf("cta %d warp %d R %d | select %lld bar %lld dyn %lld C %lld pred %lld E %lld backup %lld | levels(lane0 trees) %lld\n",
+           blockIdx.x, warp, R, phase_acc[0], phase_acc[1], phase_acc[2], phase_acc[3], phase_acc[4], phase_acc[5],
+           phase_acc[6], levels);
+#endif
 
   // ---- policy epilogue
-  for (int b = gi; b < R; b += ngroups) {
-    int action;
-    float weight;
-    rec_finish<G>(t, p, b, (long)p.batch_offset + b, a.invalid != nullptr, ga, gm, action, weight);
-    if (ga < A) a.weights_out[(long)(row0 + b) * A + ga] = weight;
-    if (ga == 0) a.action_out[row0 + b] = action;
+  for (int base = warp * gpw; base < R; base += ngroups) {
+    const bool has = base + gq < R;
+    const int b = min(base + gq, R - 1);
+    int action = 0;
+    float weight = 0.0f;
+    if (MZ_RES_WARP_UNIFORM || has)
+      rec_finish<G>(t, p, b, has, (long)p.batch_offset + b, a.invalid != nullptr, ga, action, weight);
+    if (has && ga < A) a.weights_out[(long)(row0 + b) * A + ga] = weight;
+    if (has && ga == 0) a.action_out[row0 + b] = action;
   }
 }
 
@@ -770,6 +1128,24 @@ static void* resident_kernel_ptr(int G, bool wsmem) {
     default: return wsmem ? (void*)resident_search_kernel<32, true> : (void*)resident_search_kernel<32, false>;
   }
 #undef MZ_RES_CASE
+}
+
+// Widest pair of layers evaluated in one phase (two heads of a module): columns of one TMA ring stage row.
+static int net_max_pair_cols(const Net& net) {
+  int cols = 0;
+  auto pair = [&](const mz_stack& a, const mz_stack* b) {
+    for (int l = 0; l < a.n_layers; ++l) {
+      int c = a.out_dim[l];
+      if (b != nullptr && b->n_layers == a.n_layers) c += b->out_dim[l];
+      cols = std::max(cols, c);
+    }
+    if (b != nullptr && b->n_layers != a.n_layers)
+      for (int l = 0; l < b->n_layers; ++l) cols = std::max(cols, (int)b->out_dim[l]);
+  };
+  pair(net.repr, nullptr);
+  pair(net.pred_v, &net.pred_pi);
+  pair(net.dyn_ns, &net.dyn_r);
+  return round_up(cols, 4);
 }
 
 static int net_weight_bytes(const Net& net) {
@@ -806,6 +1182,7 @@ int resident_init(ResidentState& st, const Net& net, int device, std::string* er
   if (const char* e = getenv("MZ_RESIDENT_TREES")) st.trees_per_cta = atoi(e);
   if (const char* e = getenv("MZ_RESIDENT_GLOBAL_WEIGHTS")) st.force_global_weights = atoi(e);
   if (const char* e = getenv("MZ_RESIDENT_K")) st.noise_levels = std::max(0, atoi(e));
+  if (const char* e = getenv("MZ_RESIDENT_NO_TMA")) st.no_tma_ring = atoi(e);
   if (const char* e = getenv("MZ_RESIDENT_THREADS")) {
     const int n = atoi(e);
     if (n == 64 || n == 128 || n == 256) st.threads = n;
@@ -819,6 +1196,11 @@ void resident_destroy(ResidentState& st) {
   if (st.cont_keys) cudaFree(st.cont_keys);
   if (st.rec_nodes) cudaFree(st.rec_nodes);
   if (st.rec_childs) cudaFree(st.rec_childs);
+  if (st.rec_logits) cudaFree(st.rec_logits);
+  st.rec_logits = nullptr;
+  if (st.path) cudaFree(st.path);
+  st.path = nullptr;
+  st.path_capacity = 0;
   st.noise_table = nullptr;
   st.cont_keys = nullptr;
   st.rec_nodes = st.rec_childs = nullptr;
@@ -831,7 +1213,7 @@ int resident_unpack(ResidentState& st, const Tree& tree, float gamma, std::strin
   if (!st.dirty) return 0;
   const long n = (long)tree.B * tree.N;
   resident_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st.last_stream>>>(
-      reinterpret_cast<const float4*>(st.rec_nodes), reinterpret_cast<const float4*>(st.rec_childs), tree,
+      reinterpret_cast<const float4*>(st.rec_nodes), reinterpret_cast<const float4*>(st.rec_childs), st.rec_logits, tree,
       st.last_num_sims + 1, gamma);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(st.last_stream);
@@ -844,7 +1226,7 @@ int resident_unpack(ResidentState& st, const Tree& tree, float gamma, std::strin
 }
 
 struct ResidentPlan {
-  int T = 0, grid = 0, wsmem = 0, PL = 1;
+  int T = 0, grid = 0, wsmem = 0, PL = 1, ring_stage_floats = 0;
   size_t smem = 0;
 };
 
@@ -854,11 +1236,15 @@ struct ResidentPlan {
 static ResidentPlan resident_plan(const ResidentState& st, const Net& net, int B, int NS, int max_depth) {
   ResidentPlan best;
   const int ld = round_up(net.max_width, 4);
+  const int ldh = round_up(std::max(2 * net.support_size + 1, net.num_actions), 4);
   const int wbytes = net_weight_bytes(net);
   const int budget = st.max_smem - 1024;  // per CTA (opt-in limit minus the static mbarrier + slack)
   const int PL = std::max(1, std::min(max_depth > 0 ? max_depth : NS, NS));
   for (int ws = st.force_global_weights ? 0 : 1; ws >= 0; --ws) {
-    auto bytes = [&](int T) { return (size_t)resident_layout(ws ? wbytes : 0, NS, T, ld, PL).total_floats * 4; };
+    int ring_floats = ws ? 0 : kTmaKC * net_max_pair_cols(net);
+    if (st.no_tma_ring) ring_floats = 0;
+    auto bytes = [&](int T) { return (size_t)resident_layout(ws ? wbytes : 0, NS, T, ld, ldh, ring_floats).total_floats * 4; };
+    if (ring_floats > 0 && bytes(1) > (size_t)budget) ring_floats = 0;  // no room for the ring: plain loads
     if (bytes(1) > (size_t)budget) continue;
     int T = 0;
     if (st.trees_per_cta > 0) {
@@ -875,9 +1261,17 @@ static ResidentPlan resident_plan(const ResidentState& st, const Net& net, int B
         }
         if ((long)per_sm * st.num_sms * cand >= B) break;
       }
+      if (!ws) {
+        // weights streamed from L2: every CTA re-reads the whole blob per simulation, so a CTA takes as many rows
+        // as keeps one CTA on every SM
+        int want = std::min((B + st.num_sms - 1) / st.num_sms, 16);
+        while (want > T && bytes(want) > (size_t)budget) --want;
+        T = std::max(T, want);
+      }
     }
     if (T <= 0 || bytes(T) > (size_t)budget) continue;
     best.T = T;
+    best.ring_stage_floats = ring_floats;
     best.wsmem = ws;
     best.smem = bytes(T);
     best.grid = (B + T - 1) / T;
@@ -919,16 +1313,36 @@ int resident_launch(ResidentState& st, const Net& net, const float* weights, con
   a.root_value_out = root_value_out;
   a.T = plan.T;
   a.ld = round_up(net.max_width, 4);
+  a.ldh = round_up(std::max(2 * net.support_size + 1, net.num_actions), 4);
   a.PL = plan.PL;
+  a.ring_stage_floats = plan.ring_stage_floats;
+  {
+    const size_t need = (size_t)B * plan.PL;
+    if (need > st.path_capacity) {
+      if (st.path) cudaFree(st.path);
+      st.path = nullptr;
+      st.path_capacity = 0;
+      if (cudaMalloc((void**)&st.path, need * 4) != cudaSuccess) {
+        cudaGetLastError();
+        *err = "resident engine: cudaMalloc(path scratch) failed";
+        return 1;
+      }
+      st.path_capacity = need;
+    }
+    a.path = st.path;
+  }
   a.clear_embeddings = (p.max_depth > 0 || NS + 1 < tree.N) ? 1 : 0;
   {
     const size_t nodes = (size_t)B * (NS + 1);
     if (nodes > st.rec_capacity) {
       if (st.rec_nodes) cudaFree(st.rec_nodes);
       if (st.rec_childs) cudaFree(st.rec_childs);
+      if (st.rec_logits) cudaFree(st.rec_logits);
       st.rec_nodes = st.rec_childs = nullptr;
+      st.rec_logits = nullptr;
       st.rec_capacity = 0;
-      if (cudaMalloc(&st.rec_nodes, nodes * 16) != cudaSuccess || cudaMalloc(&st.rec_childs, nodes * A * 32) != cudaSuccess) {
+      if (cudaMalloc(&st.rec_nodes, nodes * 16) != cudaSuccess || cudaMalloc(&st.rec_childs, nodes * A * 16) != cudaSuccess ||
+          cudaMalloc((void**)&st.rec_logits, nodes * A * 4) != cudaSuccess) {
         cudaGetLastError();
         *err = "resident engine: cudaMalloc(tree records) failed";
         return 1;
@@ -937,6 +1351,7 @@ int resident_launch(ResidentState& st, const Net& net, const float* weights, con
     }
     a.rec_nodes = reinterpret_cast<float4*>(st.rec_nodes);
     a.rec_childs = reinterpret_cast<float4*>(st.rec_childs);
+    a.rec_logits = st.rec_logits;
   }
   // tie-break noise ahead of the search (MuZero policy only: the Gumbel selectors ignore their key)
   if (p.policy == MZ_POLICY_MUZERO && NS > 0 && st.noise_levels > 0) {

@@ -21,13 +21,17 @@ struct ResidentState {
   int threads = 256;
   int trees_per_cta = 0;         // 0 = choose per launch (MZ_RESIDENT_TREES)
   int force_global_weights = 0;  // MZ_RESIDENT_GLOBAL_WEIGHTS
+  int no_tma_ring = 0;           // MZ_RESIDENT_NO_TMA: read streamed weights with plain loads (debug / A-B)
   int noise_levels = 32;         // tie-break noise levels produced ahead of the search (MZ_RESIDENT_K)
   float* noise_table = nullptr;  // [B][NS][K][A]
   uint32_t* cont_keys = nullptr; // [B][NS][2] carried key after K levels
   size_t noise_capacity = 0, cont_capacity = 0;
   void* rec_nodes = nullptr;     // [B][NS + 1] 16-byte node records of the last search
-  void* rec_childs = nullptr;    // [B][NS + 1][A][2] 16-byte child records
+  void* rec_childs = nullptr;    // [B][NS + 1][A] 16-byte child records
+  float* rec_logits = nullptr;   // [B][NS + 1][A] prior logits
   size_t rec_capacity = 0;       // in nodes
+  uint32_t* path = nullptr;      // [B][path slots] selected edges of the simulation in flight
+  size_t path_capacity = 0;
   bool dirty = false;            // the SoA tree view is stale: resident_unpack() refreshes it
   cudaStream_t last_stream = nullptr;
   int last_num_sims = 0;

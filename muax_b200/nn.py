@@ -202,6 +202,10 @@ def pack_stacks(stacks):
         for l, (w, b) in enumerate(layers):
             w, b = _to_numpy(w), _to_numpy(b)
             st.in_dim[l], st.out_dim[l] = w.shape
+            pad = (-off) % 4  # weight matrices start on 16-byte boundaries: the kernels fetch 4 output units per load
+            if pad:
+                chunks.append(np.zeros(pad, np.float32))
+                off += pad
             st.w_off[l] = off
             off += w.size
             st.b_off[l] = off

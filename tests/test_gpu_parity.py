@@ -158,6 +158,28 @@ def test_headline_size_invariants_and_sampled_rows(c_oracle, engine_id):
         assert_same_search({k: v[lo:lo + 32] for k, v in got.items() if k in OUT_FIELDS}, want)
 
 
+@pytest.mark.parametrize("policy,qt,A,E,H,B,NS", [(0, 0, 4, 64, (64,), 50, 16), (1, 1, 18, 64, (64, 32), 23, 12),
+                                                  (0, 0, 3, 32, (48,), 9, 20)])
+def test_resident_engine_streamed_weights(c_oracle, monkeypatch, policy, qt, A, E, H, B, NS):
+    """Wide-net mode of the CTA-resident engine: weights stay in HBM/L2 and are streamed through the TMA ring
+    (cp.async.bulk + mbarrier) — forced here on small nets with MZ_RESIDENT_GLOBAL_WEIGHTS; also with the ring
+    disabled (plain read-only loads).  Both must stay bit-identical to the C restatement."""
+    rng = np.random.default_rng(7 + A)
+    nets = make_nets(rng, 8, E, A, 21, hidden=H, bias_scale=0.05)
+    obs = rng.standard_normal((B, 8)).astype(np.float32)
+    key = np.array([5, 2000 + A], np.uint32)
+    cfg = dict(policy=policy, qtransform=qt, num_simulations=NS, support_size=10)
+    want = c_oracle.search(nets, key, obs=obs, **cfg)
+    for no_tma in ("0", "1"):
+        monkeypatch.setenv("MZ_RESIDENT_GLOBAL_WEIGHTS", "1")
+        monkeypatch.setenv("MZ_RESIDENT_NO_TMA", no_tma)
+        eng = _engine(nets, B, cfg, NS)
+        out = eng.search(key, obs=torch.from_numpy(obs).cuda(), engine=7, **_search_kwargs(cfg))
+        got = _collect(eng, *out)
+        assert_same_search(got, want)
+        check_tree_invariants(got, NS)
+
+
 def test_host_buffer_entry_point_equals_device_entry_point():
     nets, inp, cfg, want = load_golden("lunar_muzero_invalid_seed1")
     eng = _engine(nets, inp["obs"].shape[0], cfg, cfg["num_simulations"])

@@ -83,7 +83,11 @@ def test_params_layout_is_haiku_shaped_and_packs_in_order():
     blob, st = model._spec.pack(p)
     assert st["repr"].n_layers == 1 and st["dyn_r"].n_layers == 2
     assert st["repr"].w_off[0] == 0 and st["repr"].b_off[0] == 32 and st["pred_v"].w_off[0] == 40
-    assert blob.size == sum(v["w"].size + v["b"].size for g in p for v in g.values())
+    # weight matrices start on 16-byte boundaries (zero padding between layers), nothing else is added
+    payload = sum(v["w"].size + v["b"].size for g in p for v in g.values())
+    assert payload <= blob.size <= payload + 3 * 9
+    for name in ("repr", "pred_v", "pred_pi", "dyn_ns", "dyn_r"):
+        assert all(st[name].w_off[l] % 4 == 0 for l in range(st[name].n_layers))
     # stack order / content: dyn_ns is the first two dynamic linears, dyn_r the last two (muax/nn.py:97-104)
     stacks = model._spec.stacks(p)
     assert np.array_equal(stacks["dyn_r"][1][0], p.dynamic["dynamic/linear_3"]["w"])
