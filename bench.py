@@ -205,7 +205,7 @@ def run_ours(args, wl, name):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
     from muax_b200.sharded import ShardedSearch
     kw_local = {k: v for k, v in kw.items() if k not in ("global_batch", "batch_offset")}
-    sharded = ShardedSearch(lambda key, obs, **k2: eng.search(key, obs=obs, **k2), GB, A)
+    sharded = ShardedSearch(lambda key, obs, **k2: eng.search(key, obs=obs, **k2), GB, A, writes_into_out=True)
 
     def step_device(i):
         # rows [rank*B, (rank+1)*B) of the global batch; with world > 1 this ends with the one all-gather of

@@ -119,6 +119,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ raw, float* __rest
 // (key, sel) = split(key); noise[a] = 1e-7 * uniform(sel, (A,))[a]  (Appendix A.3, A.5, A.7).
 __global__ void __launch_bounds__(128) noise_table_kernel(SearchParams p, int B, int A, int K, float* __restrict__ table,
                                                           uint32_t* __restrict__ cont) {
+  // programmatic dependent launch: the search kernel that follows may start its prologue (weight staging, tree
+  // initialisation, root inference) right away; it executes griddepcontrol.wait before it first reads the table
+  asm volatile("griddepcontrol.launch_dependents;");
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int NS = p.num_simulations;
   if (idx >= B * NS) return;

@@ -396,6 +396,9 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
     }
   };
   if (use_table) {
+    // launched with programmatic stream serialisation: everything above overlapped the noise pre-pass; its table
+    // is complete and visible after this wait (a no-op without the launch attribute)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     prefetch_noise(0, 0);
     cp_async_wait_all();
   }
@@ -814,7 +817,17 @@ inline int lane2_launch(Lane2State& st, LaneState& ls, const Tree& out, const Se
   const size_t smem = st.variant->smem(ls.net.packed_floats, NS, ls.net.obs_dim, N);
   const int grid = (B + kLT - 1) / kLT;
   void* args[] = {&a};
-  const cudaError_t e = cudaLaunchKernel(st.variant->fn, dim3(grid), dim3(32 * st.warps), args, smem, stream);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(32 * st.warps);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (a.noise_table != nullptr && !getenv("MZ_NO_PDL")) ? 1 : 0;  // overlap the prologue with the noise pre-pass
+  const cudaError_t e = cudaLaunchKernelExC(&cfg, st.variant->fn, args);
   *launches += 1;
   if (e != cudaSuccess) {
     *err = std::string("lane2 engine launch failed: ") + cudaGetErrorString(e);

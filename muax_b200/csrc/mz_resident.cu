@@ -167,12 +167,52 @@ __device__ __noinline__ void dense_quads(const DenseJob A, const DenseJob B, int
 // Wide nets (C5: 1.4 MB of fp32 weights) do not fit shared memory, and a plain load per k-step leaves every FMA
 // waiting for an L2 round trip (measured: 170k cycles per Dynamic pass).  Here the weight rows of the two heads are
 // streamed through a ring of kTmaStages shared-memory stages by TMA bulk copies (cp.async.bulk + mbarrier
-// complete_tx): thread 0 keeps kTmaStages - 1 chunks of kTmaKC rows in flight while all threads run the FMA chains
-// of the current chunk out of shared memory with 128-bit loads.  Accumulation order is unchanged (k ascending).
-constexpr int kTmaKC = 16;     // weight rows per chunk
-constexpr int kTmaStages = 3;
+// complete_tx) while all threads run the FMA chains of the current chunk out of shared memory with 128-bit loads.
+// Accumulation order is unchanged (k ascending).
+//
+// Every CTA needs the same rows at about the same time, so the kernel is launched in thread-block clusters when the
+// batch divides evenly: the cluster's rank-0 CTA issues ONE multicast bulk copy per chunk that lands in all CTAs'
+// rings (same CTA-relative offset) and completes the transaction on each CTA's own `full` mbarrier — L2 traffic for
+// weights drops by the cluster size.  A stage is refilled only after every CTA of the cluster has finished reading
+// it: each CTA's thread 0 arrives (remote mbarrier arrive over DSMEM) on the leader's `empty` mbarrier of that stage.
+#ifndef MZ_TMA_KC
+#define MZ_TMA_KC 16
+#endif
+#ifndef MZ_TMA_STAGES
+#define MZ_TMA_STAGES 3
+#endif
+constexpr int kTmaKC = MZ_TMA_KC;          // weight rows per chunk (multiple of 4)
+constexpr int kTmaStages = MZ_TMA_STAGES;
 
-// mbarrier wait that cannot hang the GPU: a chunk that has not landed after ~1 s of polling is a bug -> trap.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                       uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
+// mbarrier wait that cannot hang the GPU: a phase that has not completed after ~1 s of polling is a bug -> trap.
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0;; ++spin) {
@@ -191,23 +231,52 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
 
 struct TmaRing {
   float* stage;          // kTmaStages x stage_floats (shared), or null when the ring is disabled
-  uint64_t* full;        // kTmaStages mbarriers: "chunk has landed"
+  uint64_t* full;        // kTmaStages mbarriers: "chunk has landed" (one arrival + the chunk's bytes)
+  uint64_t* empty;       // kTmaStages mbarriers, used in the cluster's rank-0 CTA: "all CTAs are done with the stage"
   int32_t stage_floats;
-  uint32_t g;            // chunks issued so far (stage = g % kTmaStages, parity = (g / kTmaStages) & 1); CTA-uniform
+  uint32_t g;            // chunks consumed so far (stage = g % kTmaStages, parity = (g / kTmaStages) & 1); uniform
+  uint32_t rank, ncta;   // position in the cluster (ncta == 1: no cluster)
+  int32_t T;             // trees per CTA (uniform over the cluster; this CTA may own fewer live rows)
 };
 
+// One chunk, thread 0 only (gi = global chunk number):
+//   1. arm this CTA's `full` barrier with the chunk's byte count;
+//   2. (consumed_gi >= 0) tell the cluster leader that this CTA is done with the chunk it has just consumed;
+//   3. the leader waits until the chunk's stage is free cluster-wide, then issues the (multicast) copies.
+// 2 comes before 3 because the leader's own arrival is one of the arrivals it waits for.
+__device__ __forceinline__ void tma_ring_step(TmaRing* ring, bool do_issue, uint32_t gi, const float* srcA,
+                                              uint32_t bytesA, const float* srcB, uint32_t bytesB, uint32_t offB_floats,
+                                              bool consumed, uint32_t consumed_gi) {
+  constexpr uint32_t S = kTmaStages;
+  const uint32_t st = gi % S;
+  float* dst = ring->stage + (size_t)st * ring->stage_floats;
+  if (do_issue) mbar_expect_tx(&ring->full[st], bytesA + bytesB);
+  if (consumed && ring->ncta > 1) mbar_arrive_remote(&ring->empty[consumed_gi % S], 0u);
+  if (!do_issue) return;
+  if (ring->ncta == 1) {
+    tma_bulk_g2s(dst, srcA, bytesA, &ring->full[st]);
+    if (bytesB) tma_bulk_g2s(dst + offB_floats, srcB, bytesB, &ring->full[st]);
+  } else if (ring->rank == 0) {
+    // chunk gi reuses the stage of chunk gi - S: its (gi / S - 1)-th consumption must be complete in every CTA
+    if (gi >= S) mbar_wait_bounded(&ring->empty[st], (gi / S - 1u) & 1u);
+    const uint16_t mask = (uint16_t)((1u << ring->ncta) - 1u);
+    tma_bulk_g2s_multicast(dst, srcA, bytesA, &ring->full[st], mask);
+    if (bytesB) tma_bulk_g2s_multicast(dst + offB_floats, srcB, bytesB, &ring->full[st], mask);
+  }
+}
+
 template <int RT, bool kVec>
-__device__ __noinline__ void dense_tma(const DenseJob A, const DenseJob B, int R, const int32_t* onehot, int act_kind,
-                                       int apply_act, TmaRing* ring) {
+__device__ __noinline__ void dense_tma(const DenseJob A, const DenseJob B, int R, int T, const int32_t* onehot,
+                                       int act_kind, int apply_act, TmaRing* ring) {
   constexpr int KC = kTmaKC, S = kTmaStages;
   const int na = A.nout, nb = B.nout, nin = A.nin;
   const int qa = (na + 3) >> 2, qtot = qa + ((nb + 3) >> 2);
-  const int tiles = (R + RT - 1) / RT, total = tiles * qtot;
+  // the pass structure depends on T (uniform over the cluster), not on this CTA's live rows
+  const int tiles = (T + RT - 1) / RT, total = tiles * qtot;
   const int nchunks = (nin + KC - 1) / KC;
   const uint32_t stage0 = smem_u32(ring->stage);
   for (int pass0 = 0; pass0 < total; pass0 += blockDim.x) {
     const int item = min(pass0 + (int)threadIdx.x, total - 1);  // a thread without an item recomputes the last one
-    const bool valid = pass0 + (int)threadIdx.x < total;
     const int tile = item / qtot;
     int q = item - tile * qtot;
     const bool second = q >= qa;
@@ -216,6 +285,7 @@ __device__ __noinline__ void dense_tma(const DenseJob A, const DenseJob B, int R
     const int nout = J.nout;
     const int j0 = q * 4;
     const int r0 = tile * RT;
+    const bool valid = pass0 + (int)threadIdx.x < total && r0 < R;
     const int c1 = min(j0 + 1, nout - 1) - j0, c2 = min(j0 + 2, nout - 1) - j0, c3 = min(j0 + 3, nout - 1) - j0;
     const uint32_t col_off = (uint32_t)((second ? KC * na : 0) + j0) * 4u;  // byte offset of the quad inside a stage
     uint32_t xa[RT];
@@ -226,22 +296,18 @@ __device__ __noinline__ void dense_tma(const DenseJob A, const DenseJob B, int R
       acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
     }
     const uint32_t g0 = ring->g;
-    auto issue = [&](int c) {
-      const uint32_t gi = g0 + (uint32_t)c;
-      const int st = (int)(gi % S);
-      const int rows = min(KC, nin - c * KC);
-      float* dst = ring->stage + (size_t)st * ring->stage_floats;
-      mbar_expect_tx(&ring->full[st], (uint32_t)(rows * (na + nb)) * 4u);
-      tma_bulk_g2s(dst, A.W + (size_t)c * KC * na, (uint32_t)(rows * na) * 4u, &ring->full[st]);
-      if (nb > 0) tma_bulk_g2s(dst + KC * na, B.W + (size_t)c * KC * nb, (uint32_t)(rows * nb) * 4u, &ring->full[st]);
+    // step(c, done): issue chunk c of this pass (if it exists) and/or report chunk `done` as consumed
+    auto step = [&](int c, int done) {
+      const bool do_issue = c < nchunks;
+      const int cc = do_issue ? c : 0;
+      const int rows = min(KC, nin - cc * KC);
+      tma_ring_step(ring, do_issue, g0 + (uint32_t)cc, A.W + (size_t)cc * KC * na, (uint32_t)(rows * na) * 4u,
+                    B.W + (size_t)cc * KC * nb, (uint32_t)(rows * nb) * 4u, (uint32_t)(KC * na), done >= 0,
+                    g0 + (uint32_t)max(done, 0));
     };
     if (threadIdx.x == 0)
-      for (int c = 0; c < min(S, nchunks); ++c) issue(c);
+      for (int c = 0; c < min(S, nchunks); ++c) step(c, -1);
     for (int c = 0; c < nchunks; ++c) {
-      if (c > 0) {
-        __syncthreads();  // every thread is done with chunk c - 1: its stage can be refilled
-        if (threadIdx.x == 0 && c + S - 1 < nchunks) issue(c + S - 1);
-      }
       const uint32_t gi = g0 + (uint32_t)c;
       mbar_wait_bounded(&ring->full[gi % S], (gi / S) & 1u);
       const uint32_t wbase = stage0 + (uint32_t)((gi % S) * ring->stage_floats) * 4u + col_off;
@@ -272,6 +338,8 @@ __device__ __noinline__ void dense_tma(const DenseJob A, const DenseJob B, int R
           }
         }
       }
+      __syncthreads();  // this CTA is done with chunk c
+      if (threadIdx.x == 0) step(c + S, c);  // report chunk c consumed; refill its stage with chunk c + S
     }
     ring->g = g0 + (uint32_t)nchunks;
     const float* wrow = J.W + (size_t)nin * nout + j0;  // one-hot rows follow the nin input rows
@@ -301,7 +369,6 @@ __device__ __noinline__ void dense_tma(const DenseJob A, const DenseJob B, int R
         }
       }
     }
-    __syncthreads();  // the last chunks' stages are free before the next pass / layer issues into them
   }
 }
 
@@ -319,12 +386,12 @@ __device__ __forceinline__ void dense_pair_auto(const DenseJob& A, const DenseJo
     // stream the weight rows through the TMA ring when the layer is long enough to pay for the pipeline
     if (ring != nullptr && ring->stage != nullptr && aligned && (A.nin & 3) == 0 && A.nin >= 2 * kTmaKC &&
         (B.nout == 0 || B.nin == A.nin) && kTmaKC * (A.nout + B.nout) <= ring->stage_floats) {
-      if (R > 4 || rt == 4) {
-        if (vec) dense_tma<4, true>(A, B, R, onehot, act_kind, apply_act, ring);
-        else dense_tma<4, false>(A, B, R, onehot, act_kind, apply_act, ring);
+      if (ring->T > 4) {
+        if (vec) dense_tma<4, true>(A, B, R, ring->T, onehot, act_kind, apply_act, ring);
+        else dense_tma<4, false>(A, B, R, ring->T, onehot, act_kind, apply_act, ring);
       } else {
-        if (vec) dense_tma<2, true>(A, B, R, onehot, act_kind, apply_act, ring);
-        else dense_tma<2, false>(A, B, R, onehot, act_kind, apply_act, ring);
+        if (vec) dense_tma<2, true>(A, B, R, ring->T, onehot, act_kind, apply_act, ring);
+        else dense_tma<2, false>(A, B, R, ring->T, onehot, act_kind, apply_act, ring);
       }
       return;
     }
@@ -881,13 +948,23 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   const int ldh = a.ldh;
   const ResidentLayout L = resident_layout(kWSmem ? a.weight_bytes : 0, NS, T, ld, ldh, kWSmem ? 0 : a.ring_stage_floats);
   __shared__ __align__(8) uint64_t ring_full[kTmaStages];
+  __shared__ __align__(8) uint64_t ring_empty[kTmaStages];
   TmaRing ring;
   ring.stage = (!kWSmem && a.ring_stage_floats > 0) ? smem + L.ring : nullptr;
   ring.full = ring_full;
+  ring.empty = ring_empty;
   ring.stage_floats = a.ring_stage_floats;
   ring.g = 0;
+  ring.rank = kWSmem ? 0u : cluster_ctarank();
+  ring.ncta = kWSmem ? 1u : cluster_nctarank();
+  ring.T = T;
   if (!kWSmem && threadIdx.x == 0)
-    for (int i = 0; i < kTmaStages; ++i) mbar_init(&ring_full[i], 1);
+    for (int i = 0; i < kTmaStages; ++i) {
+      mbar_init(&ring_full[i], 1);
+      mbar_init(&ring_empty[i], ring.ncta);
+    }
+  // barriers must exist cluster-wide before the first remote arrive / multicast (and nobody may leave early, below)
+  if (!kWSmem && ring.ncta > 1) cluster_sync_all();
   const int act_kind = a.net.activation;
 
   const float* w = a.weights;
@@ -1113,6 +1190,8 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
     if (has && ga < A) a.weights_out[(long)(row0 + b) * A + ga] = weight;
     if (has && ga == 0) a.action_out[row0 + b] = action;
   }
+  // a CTA's shared memory (the leader's `empty` barriers, everybody's ring) must outlive its peers' last accesses
+  if (!kWSmem && ring.ncta > 1) cluster_sync_all();
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1183,6 +1262,10 @@ int resident_init(ResidentState& st, const Net& net, int device, std::string* er
   if (const char* e = getenv("MZ_RESIDENT_GLOBAL_WEIGHTS")) st.force_global_weights = atoi(e);
   if (const char* e = getenv("MZ_RESIDENT_K")) st.noise_levels = std::max(0, atoi(e));
   if (const char* e = getenv("MZ_RESIDENT_NO_TMA")) st.no_tma_ring = atoi(e);
+  if (const char* e = getenv("MZ_RESIDENT_CLUSTER")) {
+    const int n = atoi(e);
+    if (n == 1 || n == 2 || n == 4 || n == 8) st.cluster_size = n;
+  }
   if (const char* e = getenv("MZ_RESIDENT_THREADS")) {
     const int n = atoi(e);
     if (n == 64 || n == 128 || n == 256) st.threads = n;
@@ -1226,7 +1309,7 @@ int resident_unpack(ResidentState& st, const Tree& tree, float gamma, std::strin
 }
 
 struct ResidentPlan {
-  int T = 0, grid = 0, wsmem = 0, PL = 1, ring_stage_floats = 0;
+  int T = 0, grid = 0, wsmem = 0, PL = 1, ring_stage_floats = 0, cluster = 1;
   size_t smem = 0;
 };
 
@@ -1267,6 +1350,18 @@ static ResidentPlan resident_plan(const ResidentState& st, const Net& net, int B
         int want = std::min((B + st.num_sms - 1) / st.num_sms, 16);
         while (want > T && bytes(want) > (size_t)budget) --want;
         T = std::max(T, want);
+        // thread-block clusters share each weight chunk through one multicast copy: needs a uniform grid (every CTA
+        // full, CTA count a multiple of the cluster size); take the nearest T that gives one, if any
+        if (ring_floats > 0 && st.cluster_size > 1) {
+          for (int cand = T; cand <= std::min(2 * T, 16); ++cand) {
+            if (bytes(cand) > (size_t)budget) break;
+            if (B % cand == 0 && (B / cand) % st.cluster_size == 0) {
+              T = cand;
+              best.cluster = st.cluster_size;
+              break;
+            }
+          }
+        }
       }
     }
     if (T <= 0 || bytes(T) > (size_t)budget) continue;
@@ -1391,8 +1486,19 @@ int resident_launch(ResidentState& st, const Net& net, const float* weights, con
     }
   }
   void* args[] = {&a};
-  const cudaError_t e = cudaLaunchKernel(resident_kernel_ptr(st.G, plan.wsmem != 0), dim3(plan.grid), dim3(st.threads),
-                                         args, plan.smem, stream);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(plan.grid);
+  cfg.blockDim = dim3(st.threads);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = plan.cluster > 1 ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelExC(&cfg, resident_kernel_ptr(st.G, plan.wsmem != 0), args);
   *launches += 1;
   if (e != cudaSuccess) {
     *err = std::string("resident engine launch failed: ") + cudaGetErrorString(e);

@@ -21,6 +21,9 @@ struct ResidentState {
   int threads = 256;
   int trees_per_cta = 0;         // 0 = choose per launch (MZ_RESIDENT_TREES)
   int force_global_weights = 0;  // MZ_RESIDENT_GLOBAL_WEIGHTS
+  int cluster_size = 1;          // CTAs per cluster sharing the streamed weights by TMA multicast (MZ_RESIDENT_CLUSTER);
+                                 // measured on B200 (C5 shapes): 1 -> 7.6 ms, 4 -> 9.1 ms, 8 -> 17.5 ms per act (lockstep
+                                 // of the cluster costs more than the L2 traffic it saves), so clusters are opt-in
   int no_tma_ring = 0;           // MZ_RESIDENT_NO_TMA: read streamed weights with plain loads (debug / A-B)
   int noise_levels = 32;         // tie-break noise levels produced ahead of the search (MZ_RESIDENT_K)
   float* noise_table = nullptr;  // [B][NS][K][A]

@@ -117,9 +117,10 @@ class SearchEngine:
         return a
 
     # ------------------------------------------------------------------ device-resident search
-    def search(self, rng_key, obs=None, root=None, invalid_actions=None, noise=None, **kw):
+    def search(self, rng_key, obs=None, root=None, invalid_actions=None, noise=None, out=None, **kw):
         """One `act` worth of search on device tensors.  Returns (action i32[B], action_weights f32[B,A],
-        root_value f32[B]) as CUDA tensors; nothing synchronises."""
+        root_value f32[B]) as CUDA tensors; nothing synchronises.  `out` = optional preallocated (action, weights,
+        root_value) tensors the kernels write into (e.g. views of one all-gather send buffer)."""
         B, A, E = self.batch, self.A, self.E
         args = self.make_args(rng_key, **kw)
         with torch.cuda.device(self.device):
@@ -135,9 +136,15 @@ class SearchEngine:
                 r_value = _dev(value, self.device, f32, (B,), "root value")
             inv_t = _dev(invalid_actions, self.device, torch.uint8, (B, A), "invalid_actions")
             noise_t = _dev(noise, self.device, f32, (B, A), "noise")
-            action = torch.empty(B, dtype=torch.int32, device=self.device)
-            weights = torch.empty(B, A, dtype=f32, device=self.device)
-            root_value = torch.empty(B, dtype=f32, device=self.device)
+            if out is not None:
+                action, weights, root_value = out
+                for t, dt, shp in ((action, torch.int32, (B,)), (weights, f32, (B, A)), (root_value, f32, (B,))):
+                    if t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous() or t.device != self.device:
+                        raise ValueError("out: expected contiguous (int32[B], float32[B,A], float32[B]) on the engine's device")
+            else:
+                action = torch.empty(B, dtype=torch.int32, device=self.device)
+                weights = torch.empty(B, A, dtype=f32, device=self.device)
+                root_value = torch.empty(B, dtype=f32, device=self.device)
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             rc = self.lib.mz_search(self._h, _ptr(obs_t), _ptr(r_logits), _ptr(r_value), _ptr(r_emb), _ptr(inv_t),
                                     _ptr(noise_t), ctypes.byref(args), _ptr(action), _ptr(weights), _ptr(root_value),

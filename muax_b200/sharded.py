@@ -37,8 +37,13 @@ class ShardedSearch:
     search_fn(rng_key, obs_local, global_batch=..., batch_offset=..., **kw) -> (action, weights, value) tensors;
     with a `SearchEngine` pass `engine.search` (observations via `obs=`)."""
 
-    def __init__(self, search_fn, global_batch, num_actions, group=None):
+    def __init__(self, search_fn, global_batch, num_actions, group=None, writes_into_out=False):
+        """writes_into_out: `search_fn` accepts `out=(action, weights, value)` and writes its results there
+        (SearchEngine.search does).  With even shards the three outputs are then views of ONE flat send buffer, so
+        the step is: search kernels -> one all-gather -> three strided copies, no packing kernels."""
         self.search_fn = search_fn
+        self.writes_into_out = bool(writes_into_out)
+        self._send = self._recv = None
         self.global_batch = int(global_batch)
         self.A = int(num_actions)
         self.group = group
@@ -54,6 +59,8 @@ class ShardedSearch:
     def act(self, rng_key, obs_local, **kw):
         if obs_local.shape[0] != self.count:
             raise ValueError(f"rank {self.rank} owns {self.count} rows, got {obs_local.shape[0]}")
+        if self.world > 1 and self.writes_into_out and self.global_batch % self.world == 0:
+            return self._act_flat(rng_key, obs_local, **kw)
         action, weights, value = self.search_fn(rng_key, obs_local, global_batch=self.global_batch,
                                                 batch_offset=self.offset, **kw)
         if self.world == 1:
@@ -71,3 +78,20 @@ class ShardedSearch:
             _, cnt = shard_bounds(self.global_batch, self.world, r)
             parts.append(self._gather_buf[r * self.max_count:r * self.max_count + cnt])
         return unpack_outputs(torch.cat(parts, dim=0))
+
+    def _act_flat(self, rng_key, obs_local, **kw):
+        n, A, W = self.count, self.A, self.world
+        row = n * (A + 2)  # floats per rank: weights [n, A] | value [n] | action [n] (int32 bits)
+        dev = obs_local.device
+        if self._send is None or self._send.device != dev:
+            self._send = torch.empty(row, dtype=torch.float32, device=dev)
+            self._recv = torch.empty(W * row, dtype=torch.float32, device=dev)
+        send = self._send
+        out = (send[n * A + n:].view(torch.int32), send[:n * A].view(n, A), send[n * A:n * A + n])
+        self.search_fn(rng_key, obs_local, global_batch=self.global_batch, batch_offset=self.offset, out=out, **kw)
+        dist.all_gather_into_tensor(self._recv, send, group=self.group)
+        r = self._recv.view(W, row)
+        weights = r[:, :n * A].reshape(W * n, A)
+        value = r[:, n * A:n * A + n].reshape(W * n)
+        action = r[:, n * A + n:].view(torch.int32).reshape(W * n)
+        return action, weights, value

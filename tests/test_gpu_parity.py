@@ -158,21 +158,24 @@ def test_headline_size_invariants_and_sampled_rows(c_oracle, engine_id):
         assert_same_search({k: v[lo:lo + 32] for k, v in got.items() if k in OUT_FIELDS}, want)
 
 
-@pytest.mark.parametrize("policy,qt,A,E,H,B,NS", [(0, 0, 4, 64, (64,), 50, 16), (1, 1, 18, 64, (64, 32), 23, 12),
+@pytest.mark.parametrize("policy,qt,A,E,H,B,NS", [(0, 0, 4, 64, (64,), 64, 16), (1, 1, 18, 64, (64, 32), 24, 12),
                                                   (0, 0, 3, 32, (48,), 9, 20)])
 def test_resident_engine_streamed_weights(c_oracle, monkeypatch, policy, qt, A, E, H, B, NS):
     """Wide-net mode of the CTA-resident engine: weights stay in HBM/L2 and are streamed through the TMA ring
-    (cp.async.bulk + mbarrier) — forced here on small nets with MZ_RESIDENT_GLOBAL_WEIGHTS; also with the ring
-    disabled (plain read-only loads).  Both must stay bit-identical to the C restatement."""
+    (cp.async.bulk + mbarrier) — forced here on small nets with MZ_RESIDENT_GLOBAL_WEIGHTS — per CTA, shared by
+    thread-block clusters of 4 / 8 CTAs through multicast copies (B = 64 and 24 give uniform grids; B = 9 does not and
+    falls back to one ring per CTA), and with the ring disabled (plain read-only loads).  All must stay bit-identical
+    to the C restatement."""
     rng = np.random.default_rng(7 + A)
     nets = make_nets(rng, 8, E, A, 21, hidden=H, bias_scale=0.05)
     obs = rng.standard_normal((B, 8)).astype(np.float32)
     key = np.array([5, 2000 + A], np.uint32)
     cfg = dict(policy=policy, qtransform=qt, num_simulations=NS, support_size=10)
     want = c_oracle.search(nets, key, obs=obs, **cfg)
-    for no_tma in ("0", "1"):
+    for no_tma, cluster in (("0", "4"), ("0", "8"), ("0", "1"), ("1", "1")):
         monkeypatch.setenv("MZ_RESIDENT_GLOBAL_WEIGHTS", "1")
         monkeypatch.setenv("MZ_RESIDENT_NO_TMA", no_tma)
+        monkeypatch.setenv("MZ_RESIDENT_CLUSTER", cluster)
         eng = _engine(nets, B, cfg, NS)
         out = eng.search(key, obs=torch.from_numpy(obs).cuda(), engine=7, **_search_kwargs(cfg))
         got = _collect(eng, *out)

@@ -32,14 +32,20 @@ def _worker(rank, world, port, global_batch, policy, out_dir):
         obs = rng.standard_normal((global_batch, 4)).astype(np.float32)
         key = np.array([0, 11], np.uint32)
 
-        def search_fn(rng_key, obs_local, global_batch, batch_offset, **kw):
+        def search_fn(rng_key, obs_local, global_batch, batch_offset, out=None, **kw):
             r = c_oracle.search(nets, rng_key, obs=obs_local.numpy(), policy=policy, qtransform=policy,
                                 num_simulations=16, global_batch=global_batch, batch_offset=batch_offset,
                                 want_tree=False, nthreads=1)
-            return (torch.from_numpy(r["action"]), torch.from_numpy(r["action_weights"]),
-                    torch.from_numpy(r["root_value"]))
+            res = (torch.from_numpy(r["action"]), torch.from_numpy(r["action_weights"]),
+                   torch.from_numpy(r["root_value"]))
+            if out is not None:  # the engine's `out=` contract: results land in the caller's (flat-buffer) views
+                for dst, src in zip(out, res):
+                    dst.copy_(src)
+                return out
+            return res
 
-        sh = ShardedSearch(search_fn, global_batch, 3)
+        # even shards take the flat path (outputs written straight into the all-gather send buffer)
+        sh = ShardedSearch(search_fn, global_batch, 3, writes_into_out=True)
         a, w, v = sh.act(key, sh.local_rows(torch.from_numpy(obs)))
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), a=a.numpy(), w=w.numpy(), v=v.numpy(),
                  offset=sh.offset, count=sh.count)
