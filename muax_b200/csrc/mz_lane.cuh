@@ -62,6 +62,7 @@ struct LaneArgs {
   float* weights_out;
   float* root_value_out;
   int32_t B, N, dump_tree;
+  int32_t walkers;  // lane2: warps that walk trees (select / expand / backup); 0 = all of them
 };
 
 __global__ void lane_pack_kernel(const float* __restrict__ raw, float* __restrict__ packed, LPackDesc d) {

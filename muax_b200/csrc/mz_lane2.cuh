@@ -282,8 +282,12 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
   if (use_tma) mbar_wait(&wbar, 0);
   __syncthreads();
 
-  const int tpw = kLT / nwarps > 0 ? kLT / nwarps : 1;
-  const bool owner = lane < tpw && warp * tpw + lane < kLT;
+  // Tree walks (select / expand / backup) are scalar per-lane code: the trees are packed onto `walkers` warps (one
+  // per scheduler by default) instead of two lanes of every warp — the same walk costs 16 / walkers times fewer
+  // warp-instructions, and with 16 walker warps the phase was issue-bound (profiles/r01_lane2_phase_clocks.txt).
+  const int WW = a.walkers > 0 ? min(a.walkers, nwarps) : nwarps;
+  const int tpw = kLT / WW > 0 ? kLT / WW : 1;
+  const bool owner = warp < WW && lane < tpw && warp * tpw + lane < kLT;
   const int ti = owner ? warp * tpw + lane : 0;
   const bool live = owner && row0 + ti < a.B;
   const int b = min(row0 + ti, a.B - 1);
@@ -744,6 +748,7 @@ inline const std::vector<Lane2Variant>& lane2_variants() {
 struct Lane2State {
   const Lane2Variant* variant = nullptr;
   int warps = 16;
+  int walkers = 4;  // MZ_LANE2_WALKERS
 };
 
 inline void lane2_init(Lane2State& st, const LaneState& ls, const Net& net, int max_smem) {
@@ -764,6 +769,8 @@ inline void lane2_init(Lane2State& st, const LaneState& ls, const Net& net, int 
     }
   if (const char* wv = getenv("MZ_LANE2_WARPS")) st.warps = atoi(wv);
   if (st.warps != 4 && st.warps != 8 && st.warps != 16) st.warps = 16;
+  if (const char* wk = getenv("MZ_LANE2_WALKERS")) st.walkers = atoi(wk);
+  if (st.walkers != 1 && st.walkers != 2 && st.walkers != 4 && st.walkers != 8 && st.walkers != 16) st.walkers = 4;
 }
 
 inline bool lane2_supported(const Lane2State& st, const LaneState& ls, const SearchParams& p) {
@@ -795,6 +802,7 @@ inline int lane2_launch(Lane2State& st, LaneState& ls, const Tree& out, const Se
   if (getenv("MZ_NO_TMA")) a.dump_tree = 2;
   a.K = std::min(16, kGNoiseFloats / A);
   if (const char* k = getenv("MZ_GROUP_K")) a.K = std::max(0, std::min(a.K, atoi(k)));
+  a.walkers = st.walkers;
   if (NS > 0 && a.K > 0) {
     const size_t pairs = (size_t)B * NS;
     if (pairs > ls.noise_capacity) {
