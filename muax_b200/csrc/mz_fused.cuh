@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(256) fused_search_kernel(FusedArgs a) {
     const int r = i / obs_dim, k = i - r * obs_dim;
     x[r * ld + k] = a.obs[(long)(row0 + r) * obs_dim + k];
   }
+  __syncthreads();  // thread 0 initialised the mbarrier: it must exist before any other thread polls it
   mbar_wait(&wbar, 0);
   __syncthreads();
 

@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(256) group_search_kernel(GroupArgs a) {
     for (int i = l; i < N * A; i += kGL) iblk[L.children_index + i] = -1;
   }
   for (int i = l; i < net.obs_dim; i += kGL) xbuf[i] = a.obs[(size_t)b * net.obs_dim + i];
+  __syncthreads();  // thread 0 initialised the mbarrier: it must exist before any other thread polls it
   mbar_wait(&wbar, 0);
   __syncthreads();  // weights + pb_c table visible; the last CTA-wide barrier
 

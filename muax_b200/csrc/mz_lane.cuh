@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(256) lane_search_kernel(LaneArgs a) {
     const int b = min(row0 + tr, a.B - 1);
     bufs.in[k * kLT + tr] = a.obs[(size_t)b * net.obs_dim + k];
   }
+  __syncthreads();  // thread 0 initialised the mbarrier: it must exist before any other thread polls it
   mbar_wait(&wbar, 0);
   __syncthreads();
 

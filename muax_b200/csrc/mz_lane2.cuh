@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
     const int tr = i / net.obs_dim, k = i - tr * net.obs_dim;
     bufIn[k * kLT + tr] = a.obs[(size_t)min(row0 + tr, a.B - 1) * net.obs_dim + k];
   }
+  __syncthreads();  // thread 0 initialised the mbarrier: it must exist before any other thread polls it
   if (use_tma) mbar_wait(&wbar, 0);
   __syncthreads();
 

@@ -22,8 +22,12 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "muax_b200", "libmzsearch.so")], cwd=tmp,
                    check=True, capture_output=True)
-    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True, check=True).stdout
+    dis = ""
+    for cubin in sorted(os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")):  # one per translation unit
+        out = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True, check=True).stdout
+        if kname in out:
+            dis = out
+            break
     # split per function
     lines_by_off = {}
     cur_fn, cur_line, in_fn = None, None, False
