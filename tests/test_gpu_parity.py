@@ -183,6 +183,31 @@ def test_resident_engine_streamed_weights(c_oracle, monkeypatch, policy, qt, A, 
         check_tree_invariants(got, NS)
 
 
+@pytest.mark.parametrize("name,obs_dim,E,A,S,hidden,minmax,B,NS,policy", [
+    ("C3 LunarLander stock", 8, 64, 4, 10, (16,), 1, 4096, 200, 0),
+    ("C3 LunarLander notebook 64-64-16", 8, 64, 4, 20, (64, 64, 16), 0, 4096, 200, 0),
+    ("C4 Gumbel", 8, 64, 4, 10, (16,), 1, 4096, 32, 1),
+    ("C5 Atari-sized heads, one GPU's shard", 256, 256, 18, 10, (256,), 1, 1024, 50, 0)])
+def test_baseline_full_sizes_on_the_resident_engine(c_oracle, name, obs_dim, E, A, S, hidden, minmax, B, NS, policy):
+    """BASELINE.json configs 2-4 at their full sizes through AUTO (= the CTA-resident engine: trees in HBM/L2, weights
+    in shared memory or streamed through the TMA ring at C5): size-independent tree invariants on every tree, and
+    bit-exact parity on sampled row blocks re-run alone through the C restatement (PRNG draws are indexed by global
+    row, so a block of rows is reproducible on its own)."""
+    rng = np.random.default_rng(17)
+    nets = make_nets(rng, obs_dim, E, A, 2 * S + 1, hidden=hidden)
+    obs = rng.standard_normal((B, obs_dim)).astype(np.float32)
+    key = np.array([0, 9], np.uint32)
+    cfg = dict(policy=policy, qtransform=0, num_simulations=NS, support_size=S, repr_minmax=minmax, dyn_minmax=minmax)
+    eng = _engine(nets, B, cfg, NS)
+    out = eng.search(key, obs=torch.from_numpy(obs).cuda(), **_search_kwargs(cfg))
+    got = _collect(eng, *out)
+    check_tree_invariants(got, NS)
+    assert np.allclose(got["action_weights"].sum(-1), 1.0, atol=1e-5)
+    for lo in (0, B // 2 + 3, B - 8):
+        want = c_oracle.search(nets, key, obs=obs[lo:lo + 8], global_batch=B, batch_offset=lo, **cfg)
+        assert_same_search({k: v[lo:lo + 8] for k, v in got.items() if k in OUT_FIELDS}, want)
+
+
 def test_host_buffer_entry_point_equals_device_entry_point():
     nets, inp, cfg, want = load_golden("lunar_muzero_invalid_seed1")
     eng = _engine(nets, inp["obs"].shape[0], cfg, cfg["num_simulations"])
