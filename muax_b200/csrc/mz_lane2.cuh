@@ -186,6 +186,37 @@ __device__ __forceinline__ float l2_head_scalar(const float* e_col) {
   return mz_inv_scaling(x);
 }
 
+// The same head split over `parts` warps (the serial version above kept one warp busy for ~2.5k cycles per simulation
+// while 7 idled): every warp recomputes the left-to-right softmax denominator (21 adds), then takes its share of the
+// quotients and products (j - S) * (e[j] / s) -> prod_col; l2_head_final sums the products left to right.  Same
+// operations in the same order as l2_head_scalar.
+template <int F, int S>
+__device__ __forceinline__ void l2_head_products(const float* e_col, float* prod_col, int part, int parts) {
+  float e[F];
+#pragma unroll
+  for (int j = 0; j < F; ++j) e[j] = e_col[j * kLT];
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < F; ++j) s = MZ_ADD(s, e[j]);
+  for (int j = part; j < F; j += parts) {
+    bool bad = false;
+    float pr = div_try(e_col[j * kLT], s, bad);
+    if (bad) pr = MZ_DIV(e_col[j * kLT], s);
+    prod_col[j * kLT] = MZ_MUL((float)(j - S), pr);
+  }
+}
+
+template <int F, int S>
+__device__ __forceinline__ float l2_head_final(const float* prod_col) {
+  float pv[F];
+#pragma unroll
+  for (int j = 0; j < F; ++j) pv[j] = prod_col[j * kLT];
+  float x = 0.0f;
+#pragma unroll
+  for (int j = 0; j < F; ++j) x = MZ_ADD(x, pv[j]);
+  return mz_inv_scaling(x);
+}
+
 // CTA barrier, or a named barrier over the first `nthreads` threads of a warp role when the roles are split.
 __device__ __forceinline__ void l2_bar(bool named, int id, int nthreads) {
   if (named)
@@ -540,25 +571,35 @@ __global__ void __launch_bounds__(512) lane2_search_kernel(LaneArgs a) {
       l2_layer2<H, F, A>(w, net.pred_v[1], net.pred_pi[1], hA, hB, bufV, bufP, lane, warp, MW);
       l2_bar(has_aux, 2, MW * 32);
       MZ_CLK(6);  // pred layer 2 + barrier
+      // categorical heads: exps -> barrier -> quotients and products (logit buffers are free again) -> barrier -> sum
+      const int half = MW / 2;
       if (has_aux) {
         l2_head_exps<F>(bufV + lane, bufEv + lane, warp, MW);
+      } else if (warp < half) {
+        l2_head_exps<F>(bufR + lane, bufEr + lane, warp, half);
       } else {
-        const int half = MW / 2;
-        if (warp < half)
-          l2_head_exps<F>(bufR + lane, bufEr + lane, warp, half);
-        else
-          l2_head_exps<F>(bufV + lane, bufEv + lane, warp - half, MW - half);
+        l2_head_exps<F>(bufV + lane, bufEv + lane, warp - half, MW - half);
       }
       l2_bar(has_aux, 2, MW * 32);
       MZ_CLK(7);  // exps + barrier
-      if (warp == 0) sc_value[lane] = l2_head_scalar<F, S>(bufEv + lane);
-      if (!has_aux && warp == MW / 2) sc_reward[lane] = l2_head_scalar<F, S>(bufEr + lane);
+      if (has_aux) {
+        l2_head_products<F, S>(bufEv + lane, bufV + lane, warp, MW);
+      } else if (warp < half) {
+        l2_head_products<F, S>(bufEr + lane, bufR + lane, warp, half);
+      } else {
+        l2_head_products<F, S>(bufEv + lane, bufV + lane, warp - half, MW - half);
+      }
+      l2_bar(has_aux, 2, MW * 32);
+      if (warp == 0) sc_value[lane] = l2_head_final<F, S>(bufV + lane);
+      if (!has_aux && warp == half) sc_reward[lane] = l2_head_final<F, S>(bufR + lane);
       MZ_CLK(8);  // head scalar
     } else {
       // aux warps: reward head, off the critical path
       l2_head_exps<F>(bufR + lane, bufEr + lane, warp - MW, AW);
       l2_bar(true, 1, AW * 32);
-      if (warp == MW) sc_reward[lane] = l2_head_scalar<F, S>(bufEr + lane);
+      l2_head_products<F, S>(bufEr + lane, bufR + lane, warp - MW, AW);
+      l2_bar(true, 1, AW * 32);
+      if (warp == MW) sc_reward[lane] = l2_head_final<F, S>(bufR + lane);
     }
     cp_async_wait_all();
     __syncthreads();
