@@ -307,3 +307,27 @@ def test_error_paths():
     with pytest.raises(ValueError):
         muax_b200.MuZero(nn.create_muzero_network(nn.Representation, nn.Prediction, nn.Dynamic, 8, 2, 21),
                          policy="alphazero")
+
+
+def test_vector_actor_on_the_gpu_search():
+    """§8(f) rank 1: the vectorised acting loop (CartPoleVec -> MuZero.act(obs_from_batch=True) -> BatchedPNStep ->
+    TrajectoryStore) on the real search; the search inside it must equal a direct `act` on the same key and batch."""
+    import muax_b200
+    from muax_b200 import nn
+    from muax_b200.actor import CartPoleVec, TrajectoryStore, VectorActor
+    net = nn.create_muzero_network(nn.Representation, nn.Prediction, nn.Dynamic, 8, 2, 21)
+    model = muax_b200.MuZero(net, policy="muzero", discount=0.997, support_size=10)
+    model.init(muax_b200.random.PRNGKey(0), np.zeros((1, 4), np.float32))
+    env = CartPoleVec(256, seed=3)
+    store = TrajectoryStore(4096, random_seed=0)
+    actor = VectorActor(model, env, store, n=5, gamma=0.997, k_steps=5, num_simulations=16)
+    for t in range(40):
+        obs = actor.obs.copy()
+        key = muax_b200.random.PRNGKey(100 + t)
+        a, pi, v, done = actor.step(key)
+        a2, pi2, v2 = model.act(key, obs, with_pi=True, with_value=True, obs_from_batch=True, num_simulations=16)
+        assert np.array_equal(a, a2) and np.array_equal(pi, pi2) and np.array_equal(v, v2)
+        assert a.shape == (256,) and set(np.unique(a)) <= {0, 1} and np.allclose(pi.sum(-1), 1.0, atol=1e-6)
+    assert actor.episodes > 0 and len(store) > 0
+    batch = store.sample(batch_size=32, k_steps=5)
+    assert batch.obs.shape == (32, 5, 4) and batch.pi.shape == (32, 5, 2) and np.all(batch.w >= 0)
