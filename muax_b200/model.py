@@ -181,6 +181,15 @@ class MuZero:
             return action, weights
         return action
 
+    def act_device(self, rng_key, obs, num_simulations: int = 5, temperature: float = 1.0, **kw):
+        """`act` for device-resident loops (muax_b200/actor_device.py): `obs` is a CUDA float32 tensor [B, ...];
+        returns CUDA tensors (action i32[B], action_weights f32[B,A], root_value f32[B]) without synchronising."""
+        if not isinstance(obs, torch.Tensor) or not obs.is_cuda:
+            raise ValueError("act_device expects a CUDA tensor; use act() for host observations")
+        plan_output, root_value = self._plan(self._params, rng_key, obs.to(torch.float32), num_simulations=num_simulations,
+                                             temperature=temperature, **kw)
+        return plan_output.action, plan_output.action_weights, root_value
+
     def _plan(self, params, rng_key, obs, num_simulations=5, temperature=1.0, invalid_actions=None, max_depth=None,
               qtransform=None, dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25, pb_c_base=19652,
               **extra):  # muax/model.py:222-243

@@ -123,3 +123,33 @@ def test_vector_actor_loop_fills_the_store():
         assert ep.Rn[-1] == 1.0
     batch = store.sample(batch_size=16, k_steps=4)
     assert batch.obs.shape == (16, 4, 4) and batch.pi.shape == (16, 4, 2)
+
+
+def test_device_pnstep_matches_reference_pins_on_cpu_torch(pins):
+    """The torch tracer of the device-resident loop (fixed-shape outputs + mask), run here on torch's CPU device:
+    every valid slot, in slot order, must be the reference's pop — exact fields exactly, Rn / w to 1e-12 (the device
+    version sums the discounted rewards in a different association order than np.sum)."""
+    torch = pytest.importorskip("torch")
+    from muax_b200.actor_device import DevicePNStep
+    p = pins
+    T, B = p["a"].shape
+    tracer = DevicePNStep(B, int(p["n"]), float(p["gamma"]), float(p["alpha"]), device="cpu")
+    got = {f: [[] for _ in range(B)] for f in FIELDS + ("t",)}
+    for t in range(T):
+        tr, mask = tracer.add(torch.from_numpy(p["obs"][t]), torch.from_numpy(p["a"][t]), torch.from_numpy(p["r"][t]),
+                              torch.from_numpy(p["done"][t]), torch.from_numpy(p["v"][t]), torch.from_numpy(p["pi"][t]))
+        mask = mask.numpy()
+        for b in range(B):
+            for k in np.nonzero(mask[b])[0]:
+                for f in FIELDS:
+                    got[f][b].append(getattr(tr, f)[b, k].numpy())
+                got["t"][b].append(t)
+    for b in range(B):
+        assert np.array_equal(np.asarray(got["t"][b]), p[f"pop_t_{b}"]), b
+        for f in FIELDS:
+            want = p[f"pop_{f}_{b}"]
+            have = np.asarray(got[f][b]).reshape(want.shape)
+            if f in ("Rn", "w"):
+                np.testing.assert_allclose(have, want, rtol=1e-12, atol=1e-12, err_msg=f"{b} {f}")
+            else:
+                assert np.array_equal(have.astype(want.dtype), want), (b, f)

@@ -331,3 +331,43 @@ def test_vector_actor_on_the_gpu_search():
     assert actor.episodes > 0 and len(store) > 0
     batch = store.sample(batch_size=32, k_steps=5)
     assert batch.obs.shape == (32, 5, 4) and batch.pi.shape == (32, 5, 2) and np.all(batch.w >= 0)
+
+
+def test_device_actor_equals_numpy_actor_data_path():
+    """Device-resident acting loop (CartPoleVecTorch + DevicePNStep on the GPU): the episodes it stores must be what
+    the reference-pinned NumPy tracer produces from the same per-step (obs, a, r, done, v, pi) stream."""
+    import muax_b200
+    from muax_b200 import nn
+    from muax_b200.actor import BatchedPNStep, TrajectoryStore
+    from muax_b200.actor_device import CartPoleVecTorch, DeviceActor
+    net = nn.create_muzero_network(nn.Representation, nn.Prediction, nn.Dynamic, 8, 2, 21)
+    model = muax_b200.MuZero(net, policy="muzero", discount=0.997, support_size=10)
+    model.init(muax_b200.random.PRNGKey(0), np.zeros((1, 4), np.float32))
+    B = 128
+    env = CartPoleVecTorch(B, seed=5)
+    store = TrajectoryStore(100000, random_seed=0)
+    actor = DeviceActor(model, env, store, n=5, gamma=0.997, k_steps=1, num_simulations=8)
+    ref = BatchedPNStep(B, 5, 0.997, 0.5)
+    ref_eps, pending = [], [[] for _ in range(B)]
+    for t in range(45):
+        obs = actor.obs.cpu().numpy()
+        a, pi, v, done = actor.step(muax_b200.random.PRNGKey(t))
+        a, pi, v, done = a.cpu().numpy(), pi.cpu().numpy(), v.cpu().numpy(), done.cpu().numpy()
+        env_idx, tr = ref.add(obs, a, np.ones(B), done, v, pi)
+        for i, e in enumerate(env_idx):
+            pending[e].append(i)
+        rows_by_env = pending
+        pending = [[] for _ in range(B)]
+        for e in range(B):
+            if rows_by_env[e]:
+                ref.__dict__.setdefault("_blocks", {}).setdefault(e, []).append(tr[np.array(rows_by_env[e])])
+        for e in np.nonzero(done)[0]:
+            blocks = ref.__dict__["_blocks"].pop(e)
+            ref_eps.append(type(tr)(*(np.concatenate(c) for c in zip(*blocks))))
+    assert len(store) == len(ref_eps) > 0 and actor.episodes == len(ref_eps)
+    for have, want in zip(store, ref_eps):
+        assert len(have) == len(want)
+        for f in ("obs", "a", "r", "done", "v", "pi"):
+            assert np.array_equal(np.asarray(getattr(have, f)).astype(getattr(want, f).dtype), getattr(want, f)), f
+        np.testing.assert_allclose(have.Rn, want.Rn, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(have.w, want.w, rtol=1e-9, atol=1e-12)
