@@ -555,9 +555,10 @@ __global__ void __launch_bounds__(128) resident_noise_kernel(SearchParams p, int
 // an unexpanded edge has reward = value = 0, so reward + gamma * value is the same +0 as mctx's 0 + 0 * 0.
 // The mctx SoA view of the C ABI (mz_get_tree) is produced on demand by resident_unpack_kernel.
 //
-// Cache policy: the records are the only data with reuse (every simulation re-walks the top of its tree), so they
-// carry an L2 evict_last hint; embeddings and the tie-break noise are touched once per simulation and stream
-// (ld.cs / st.cs) so that they do not push the records out of the 126 MB L2.
+// Cache policy: the records are the only data with reuse (every simulation re-walks the top of its tree); embeddings
+// and the tie-break noise are touched once per simulation and stream (ld.cs / st.cs) so that they do not push the
+// records out of the 126 MB L2 — measured on B200 at the C3 shapes: 24.5 -> 22.3 ms per act (an additional L2
+// evict_last hint on the record accesses, MZ_RES_REC_HINT, changes nothing on top of that and stays off).
 //
 // Warp discipline: every lane of a warp runs the same loops (a group without a live tree, or whose walk has ended,
 // is predicated off), so all shuffles use the full mask with width G — no per-group mask convergence checks.
@@ -600,10 +601,10 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
 #define MZ_RES_REC_HINT 0
 #endif
 #ifndef MZ_RES_STREAM_NOISE
-#define MZ_RES_STREAM_NOISE 0
+#define MZ_RES_STREAM_NOISE 1
 #endif
 #ifndef MZ_RES_STREAM_EMB
-#define MZ_RES_STREAM_EMB 0
+#define MZ_RES_STREAM_EMB 1
 #endif
 #if MZ_RES_STREAM_NOISE
 #define MZ_LD_NOISE(p) __ldcs(p)
@@ -948,8 +949,27 @@ __host__ __device__ inline ResidentLayout resident_layout(int weight_bytes_in_sm
 #define MZ_RES_MIN_CTAS 3  // 80 registers per thread, three 256-thread CTAs per SM (measured: 1-4% faster than 4 x 64)
 #endif
 
+// The dense-layer drivers are real (noinline) functions that take the layer stacks by reference.  Referencing the
+// stacks inside the kernel parameter would make the compiler copy the whole 1.4 KB ResidentArgs into every thread's
+// local memory (3 CTAs x 256 threads x 1.6 KB = 1.2 MB per SM: it thrashed L1 — ncu: 64 % local-load hit rate — and
+// put an L2 round trip behind every parameter read of the tree walk).  The stacks are copied once into shared memory
+// with constant indices instead, and nothing ever takes the address of the parameter.
+struct NetStacks {
+  mz_stack repr, pred_v, pred_pi, dyn_ns, dyn_r;
+};
+__device__ __forceinline__ void copy_stack(mz_stack& dst, const mz_stack& src) {
+  dst.n_layers = src.n_layers;
+#pragma unroll
+  for (int l = 0; l < MZ_MAX_LAYERS; ++l) {
+    dst.in_dim[l] = src.in_dim[l];
+    dst.out_dim[l] = src.out_dim[l];
+    dst.w_off[l] = src.w_off[l];
+    dst.b_off[l] = src.b_off[l];
+  }
+}
+
 template <int G, bool kWSmem>
-__global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(ResidentArgs a) {
+__global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(const __grid_constant__ ResidentArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t wbar;
   constexpr bool kLdg = !kWSmem;
@@ -980,6 +1000,14 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   // barriers must exist cluster-wide before the first remote arrive / multicast (and nobody may leave early, below)
   if (!kWSmem && ring.ncta > 1) cluster_sync_all();
   const int act_kind = a.net.activation;
+  __shared__ NetStacks net;
+  if (threadIdx.x == 0) {
+    copy_stack(net.repr, a.net.repr);
+    copy_stack(net.pred_v, a.net.pred_v);
+    copy_stack(net.pred_pi, a.net.pred_pi);
+    copy_stack(net.dyn_ns, a.net.dyn_ns);
+    copy_stack(net.dyn_r, a.net.dyn_r);
+  }
 
   const float* w = a.weights;
   if constexpr (kWSmem) {
@@ -1056,7 +1084,7 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
   if constexpr (kWSmem) mbar_wait(&wbar, 0);
   __syncthreads();
   if (a.obs != nullptr) {
-    run_stacks<kLdg>(a.net.repr, nullptr, w, act_kind, x, ld, obs_dim, nullptr, ns, nullptr, ld, ld, ta0, ta1, nullptr,
+    run_stacks<kLdg>(net.repr, nullptr, w, act_kind, x, ld, obs_dim, nullptr, ns, nullptr, ld, ld, ta0, ta1, nullptr,
                      nullptr, ld, R, &ring);
     if (a.net.repr_minmax) {
       for (int r = warp; r < R; r += nwarps) min_max_row_warp(ns + r * ld, E, lane);
@@ -1064,7 +1092,7 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
     }
   }
   if (a.obs != nullptr || a.root_logits == nullptr) {
-    run_stacks<kLdg>(a.net.pred_v, &a.net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ldh, ldh, ta0, ta1, tb0,
+    run_stacks<kLdg>(net.pred_v, &net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ldh, ldh, ta0, ta1, tb0,
                      tb1, ld, R, &ring);
     for (int r = warp; r < R; r += nwarps) {
       const float v = support_to_scalar_warp(headV + r * ldh, S, lane);
@@ -1150,7 +1178,7 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
     __syncthreads();
     MZ_RCLK(1);
     // B: Dynamic (muax/model.py:269-271): next state -> ns, reward logits -> headR
-    run_stacks<kLdg>(a.net.dyn_ns, &a.net.dyn_r, w, act_kind, x, ld, E, sel_action, ns, headR, ld, ldh, ta0, ta1, tb0, tb1,
+    run_stacks<kLdg>(net.dyn_ns, &net.dyn_r, w, act_kind, x, ld, E, sel_action, ns, headR, ld, ldh, ta0, ta1, tb0, tb1,
                      ld, R, &ring);
     MZ_RCLK(2);
     // C: min-max of the next state + reward support transform, one warp per row
@@ -1162,7 +1190,7 @@ __global__ void __launch_bounds__(256, MZ_RES_MIN_CTAS) resident_search_kernel(R
     __syncthreads();
     MZ_RCLK(3);
     // D: Prediction (model.py:272): value logits -> headV, policy logits -> headP
-    run_stacks<kLdg>(a.net.pred_v, &a.net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ldh, ldh, ta0, ta1, tb0,
+    run_stacks<kLdg>(net.pred_v, &net.pred_pi, w, act_kind, ns, ld, E, nullptr, headV, headP, ldh, ldh, ta0, ta1, tb0,
                      tb1, ld, R, &ring);
     MZ_RCLK(4);
     // E: value support transform, one warp per row
@@ -1265,7 +1293,7 @@ int resident_init(ResidentState& st, const Net& net, int device, std::string* er
   st.G = G;
   for (int ws = 0; ws < 2; ++ws) {
     const cudaError_t e = cudaFuncSetAttribute(resident_kernel_ptr(G, ws != 0),
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, st.max_smem - 1024);
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, st.max_smem - 2048);
     if (e != cudaSuccess) {
       *err = std::string("resident engine: cudaFuncSetAttribute failed: ") + cudaGetErrorString(e);
       cudaGetLastError();
@@ -1335,7 +1363,7 @@ static ResidentPlan resident_plan(const ResidentState& st, const Net& net, int B
   const int ld = round_up(net.max_width, 4);
   const int ldh = round_up(std::max(2 * net.support_size + 1, net.num_actions), 4);
   const int wbytes = net_weight_bytes(net);
-  const int budget = st.max_smem - 1024;  // per CTA (opt-in limit minus the static mbarrier + slack)
+  const int budget = st.max_smem - 2048;  // per CTA (opt-in limit minus static shared memory: layer stacks, mbarriers)
   const int PL = std::max(1, std::min(max_depth > 0 ? max_depth : NS, NS));
   for (int ws = st.force_global_weights ? 0 : 1; ws >= 0; --ws) {
     int ring_floats = ws ? 0 : kTmaKC * net_max_pair_cols(net);
