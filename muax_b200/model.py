@@ -53,6 +53,8 @@ class MuZero:
         self._spec = None
         self._engines = {}
         self._weights_version = 0
+        self._learner = None
+        self._learner_version = -1
 
     # ------------------------------------------------------------------ parameters
     def init(self, rng_key, sample_input):  # muax/model.py:62-80
@@ -81,8 +83,20 @@ class MuZero:
         return self._opt_state
 
     def update(self, batch, *args, **kwargs):  # muax/model.py:181-201
-        raise NotImplementedError("the learner is outside this round's accelerated hot path (DESIGN.md); update the "
-                                  "parameters elsewhere and assign them to `model.params`")
+        """One optimisation step on a `[B, L, ...]` transition batch (the reference's default loss and optimiser,
+        re-hosted on torch autograd — muax_b200/learner.py).  Returns {'loss': ...} like the reference."""
+        from .learner import Learner, Optimizer
+        if self.loss_fn is not None:
+            raise NotImplementedError("custom loss_fn callables are jax functions in the reference; only the default "
+                                      "loss is re-hosted (muax_b200/learner.py)")
+        if self._learner is None or self._learner_version != self._weights_version:
+            opt = self._optimizer if isinstance(self._optimizer, Optimizer) else (
+                self._learner.opt if self._learner is not None else Optimizer())
+            self._learner = Learner(self, opt=opt, device=self._device)
+        out = self._learner.update(batch)
+        self._learner_version = self._weights_version  # push() bumped it: the learner's copy is still current
+        self._opt_state = self._learner.opt
+        return out
 
     def save(self, file):
         """Parameters as a flat .npz (`<group>/<module>/<w|b>`): readable without JAX (cf. model.py:203-212)."""

@@ -121,8 +121,9 @@ def test_released_constructor_shape_and_custom_architecture(tmp_path):
     for g0, g1 in zip(p, other.params):
         for k in g0:
             assert np.array_equal(g0[k]["w"], g1[k]["w"])
-    with pytest.raises(NotImplementedError):
-        model.update(None)
+    with pytest.raises(NotImplementedError):  # only the reference's default loss is re-hosted (muax_b200/learner.py)
+        muax_b200.MuZero(nn._init_representation_func(Rep, 10), nn._init_prediction_func(Pred, 4, 41),
+                         nn._init_dynamic_func(Dyn, 10, 4, 41), loss_fn=lambda *a: 0.0).update(None)
 
 
 def test_support_transform_helpers_roundtrip():
