@@ -47,6 +47,7 @@ extern "C" {
 #define MZ_ENGINE_FUSED_GROUP 4 /* the warp-autonomous variant explicitly (8 lanes per tree, packed weights) */
 #define MZ_ENGINE_FUSED_LANE 5  /* the lane == tree variant explicitly (scalar tree code, any A <= 32) */
 #define MZ_ENGINE_FUSED_LANE2 6 /* its compile-time specialisation for the stock MLP shapes (MuZero policy) */
+#define MZ_ENGINE_FUSED_WARP 8  /* warp-autonomous specialisation: a warp owns 4 trees, no CTA barrier in the loop */
 #define MZ_ENGINE_RESIDENT 7    /* one launch per act, a CTA owns T trees kept in HBM/L2 (any shapes, any root mode) */
 
 /* One hk.Sequential of hk.Linear layers with an activation between layers (none after the last):

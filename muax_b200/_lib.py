@@ -15,6 +15,7 @@ ACT_ELU, ACT_RELU = 0, 1
 ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_FUSED, ENGINE_FUSED_CTA, ENGINE_FUSED_GROUP, ENGINE_FUSED_LANE = 0, 1, 2, 3, 4, 5
 ENGINE_FUSED_LANE2 = 6
 ENGINE_RESIDENT = 7
+ENGINE_FUSED_WARP = 8
 
 EXPORTS = ("mz_last_error", "mz_default_args", "mz_create", "mz_destroy", "mz_set_weights", "mz_search",
            "mz_search_host", "mz_begin", "mz_select", "mz_expand_backup", "mz_finish", "mz_get_tree",

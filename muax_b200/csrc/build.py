@@ -13,7 +13,7 @@ ROOT = os.path.dirname(PKG)
 OUT = os.environ.get("MZ_LIB_OUT") or os.path.join(PKG, "libmzsearch.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
 HEADERS = [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_fused.cuh", "mz_group.cuh", "mz_lane.cuh",
-                                            "mz_lane2.cuh", "mz_resident.cuh")] + [
+                                            "mz_lane2.cuh", "mz_warp.cuh", "mz_resident.cuh")] + [
     os.path.join(ROOT, "include", f) for f in ("mz_math.h", "mzsearch.h")]
 # translation unit -> the headers it includes (a TU is rebuilt when it or one of these is newer than its object)
 UNITS = {

@@ -115,23 +115,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ raw, float* __rest
 
 // ---------------------------------------------------------------------------------------- tie-break noise table
 
-// One thread per (tree, simulation): per-tree key = split(sim_key, B_global)[global row]; then per level
-// (key, sel) = split(key); noise[a] = 1e-7 * uniform(sel, (A,))[a]  (Appendix A.3, A.5, A.7).
-__global__ void __launch_bounds__(128) noise_table_kernel(SearchParams p, int B, int A, int K, float* __restrict__ table,
-                                                          uint32_t* __restrict__ cont) {
-  // programmatic dependent launch: the search kernel that follows may start its prologue (weight staging, tree
-  // initialisation, root inference) right away; it executes griddepcontrol.wait before it first reads the table
-  asm volatile("griddepcontrol.launch_dependents;");
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int NS = p.num_simulations;
-  if (idx >= B * NS) return;
-  const int b = idx / NS, sim = idx - b * NS;
+// Tie-break noise of one (tree, simulation) for the first `levels` levels of its walk: per-tree key =
+// split(sim_key, B_global)[global row]; then per level (key, sel) = split(key); noise[a] = 1e-7 *
+// uniform(sel, (A,))[a]  (Appendix A.3, A.5, A.7).  `cont` receives the key the chain continues from.
+__device__ __forceinline__ void noise_row(const SearchParams& p, int A, int levels, int sim, uint32_t global_row,
+                                          float* __restrict__ row, uint32_t* __restrict__ cont) {
   uint32_t k0, k1;
-  split_key(p.sim_keys[2 * sim], p.sim_keys[2 * sim + 1], (uint32_t)p.global_batch, (uint32_t)(p.batch_offset + b),
-            p.prng_mode, k0, k1);
-  float* row = table + (size_t)idx * kGNoiseFloats;
+  split_key(p.sim_keys[2 * sim], p.sim_keys[2 * sim + 1], (uint32_t)p.global_batch, global_row, p.prng_mode, k0, k1);
   const int half = (A + 1) >> 1;
-  for (int d = 0; d < K; ++d) {
+  for (int d = 0; d < levels; ++d) {
     uint32_t n0, n1, s0, s1;
     if (p.prng_mode == MZ_PRNG_THREEFRY_LEGACY) {
       uint32_t p0, p1, q0, q1;
@@ -156,8 +148,25 @@ __global__ void __launch_bounds__(128) noise_table_kernel(SearchParams p, int B,
     k0 = n0;
     k1 = n1;
   }
-  cont[2 * (size_t)idx] = k0;
-  cont[2 * (size_t)idx + 1] = k1;
+  cont[0] = k0;
+  cont[1] = k1;
+}
+
+// One thread per (tree, simulation).
+__global__ void __launch_bounds__(128) noise_table_kernel(SearchParams p, int B, int A, int K, float* __restrict__ table,
+                                                          uint32_t* __restrict__ cont) {
+  // programmatic dependent launch: the search kernel that follows may start its prologue (weight staging, tree
+  // initialisation, root inference) right away; it executes griddepcontrol.wait before it first reads the table
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NS = p.num_simulations;
+  if (idx >= B * NS) return;
+  // simulation-major: a warp works on one simulation of 32 trees, so the depth bound below is warp-uniform
+  const int sim = idx / B, b = idx - sim * B;
+  const size_t pair = (size_t)b * NS + sim;
+  // simulation `sim` walks a tree of sim + 1 nodes: its path has at most sim + 1 levels (and then never reaches the
+  // continuation key, which is only read at depth K)
+  noise_row(p, A, min(K, sim + 1), sim, (uint32_t)(p.batch_offset + b), table + pair * kGNoiseFloats, cont + 2 * pair);
 }
 
 // ---------------------------------------------------------------------------------------- per-tree shared memory block

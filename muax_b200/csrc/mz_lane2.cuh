@@ -234,8 +234,8 @@ __device__ __noinline__ void l2_noise_cold(const uint32_t* sim_key, uint32_t glo
   uint32_t k0 = __float_as_uint(slot[0]), k1 = __float_as_uint(slot[1]);
   if (K < 0 && depth == 0) split_key(sim_key[0], sim_key[1], global_batch, global_row, prng_mode, k0, k1);
   if (K >= 0 && depth == K) {
-    k0 = __ldg(cont);
-    k1 = __ldg(cont + 1);
+    k0 = cont[0];  // generic loads: the warp engine keeps the continuation keys in shared memory
+    k1 = cont[1];
   }
   uint32_t s0, s1;
   lt_split2(k0, k1, prng_mode, k0, k1, s0, s1);

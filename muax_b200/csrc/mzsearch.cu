@@ -20,6 +20,7 @@
 #include "mz_group.cuh"
 #include "mz_lane.cuh"
 #include "mz_lane2.cuh"
+#include "mz_warp.cuh"
 #include "mz_resident.cuh"
 
 namespace mz {
@@ -332,6 +333,7 @@ struct mz_handle {
   mz::GroupState group;
   mz::LaneState lanes;
   mz::Lane2State lane2;
+  mz::WarpState warpeng;
   mz::ResidentState resident;
 };
 
@@ -559,19 +561,21 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   const bool group_ok = have_w && group_supported(h->group, h->params, h->cfg.batch);
   const bool fused_ok = have_w && fused_supported(h->fused, h->net, h->params);
   const bool lane2_ok = lane_ok && lane2_supported(h->lane2, h->lanes, h->params);
+  const bool warp_ok = have_w && h->lanes.available && warp_supported(h->warpeng, h->lanes, h->params, h->cfg.batch);
   const bool resident_ok = h->weights != nullptr && resident_supported(h->resident, h->net, h->cfg.batch, h->params.num_simulations);
-  enum { kLane = 100, kLane2 = 101 };
-  // AUTO: the shared-memory engines when the trees fit on chip (measured on B200, profiles/: lane2 0.48 ms, group
-  // 0.72 ms per act at the headline shapes), else the CTA-resident engine (trees in HBM/L2, one launch per act);
+  enum { kLane = 100, kLane2 = 101, kWarp = 102 };
+  // AUTO: the shared-memory engines when the trees fit on chip (measured on B200, profiles/: warp engine first, then
+  // lane2 0.43 ms, group 0.72 ms per act at the headline shapes), else the CTA-resident engine (trees in HBM/L2, one launch per act);
   // the stepwise engine remains for the callback mode and as the reference implementation of the kernels.
   if (engine == MZ_ENGINE_AUTO)
-    engine = (lane2_ok || group_ok) ? MZ_ENGINE_FUSED
+    engine = (warp_ok || lane2_ok || group_ok) ? MZ_ENGINE_FUSED
                                     : (resident_ok ? MZ_ENGINE_RESIDENT
                                                    : ((lane_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE));
   if (engine == MZ_ENGINE_FUSED)
-    engine = lane2_ok ? (int)kLane2 : (group_ok ? MZ_ENGINE_FUSED_GROUP : (lane_ok ? (int)kLane : MZ_ENGINE_FUSED_CTA));
+    engine = warp_ok ? (int)kWarp : lane2_ok ? (int)kLane2 : (group_ok ? MZ_ENGINE_FUSED_GROUP : (lane_ok ? (int)kLane : MZ_ENGINE_FUSED_CTA));
   if (engine == MZ_ENGINE_FUSED_LANE) engine = kLane;
   if (engine == MZ_ENGINE_FUSED_LANE2) engine = kLane2;
+  if (engine == MZ_ENGINE_FUSED_WARP) engine = kWarp;
   if (engine == MZ_ENGINE_RESIDENT) {
     if (!resident_ok) return fail("the resident engine does not support this configuration (see DESIGN.md)");
     if (obs != nullptr && h->cfg.obs_dim <= 0)
@@ -581,14 +585,22 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
     if (resident_launch(h->resident, h->net, h->weights, h->tree, h->params, obs, root_emb, root_logits, root_value,
                         invalid, noise, action_out, weights_out, root_value_out, stream, &h->launches, &err))
       return fail(err);
-  } else if (engine == kLane || engine == kLane2 || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
+  } else if (engine == kLane || engine == kLane2 || engine == kWarp || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
     if ((engine == MZ_ENGINE_FUSED_CTA && !fused_ok) || (engine == MZ_ENGINE_FUSED_GROUP && !group_ok) ||
-        (engine == kLane && !lane_ok) || (engine == kLane2 && !lane2_ok))
-      return fail("the fused engine does not support this configuration (see DESIGN.md)");
+        (engine == kLane && !lane_ok) || (engine == kLane2 && !lane2_ok) || (engine == kWarp && !warp_ok))
+      return fail(std::string("the fused engine does not support this configuration (see DESIGN.md)") +
+                  (engine == kWarp ? (h->warpeng.variant == nullptr ? " [warp engine: no compiled shape variant]"
+                                                                    : (h->lanes.available ? " [warp engine: policy / qtransform / size]"
+                                                                                        : " [warp engine: lane packing unavailable]"))
+                                   : ""));
     h->has_invalid = invalid != nullptr;
     if (args->num_simulations + 1 < h->N && clear_tree(h, args->num_simulations, true, stream)) return 1;
     std::string err;
-    if (engine == kLane2) {
+    if (engine == kWarp) {
+      if (warp_launch(h->warpeng, h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
+                      root_value_out, stream, &h->launches, &err))
+        return fail(err);
+    } else if (engine == kLane2) {
       if (lane2_launch(h->lane2, h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
                        root_value_out, stream, &h->launches, &err))
         return fail(err);
@@ -784,6 +796,7 @@ int mz_create(mz_handle** out, const mz_config* cfg) {
       return fail(err);
     }
     lane2_init(h->lane2, h->lanes, h->net, h->lanes.max_smem);
+    warp_init(h->warpeng, h->lanes, h->net, h->lanes.max_smem);
   }
 #undef MZ_TRY
   *out = h;

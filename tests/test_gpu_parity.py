@@ -47,7 +47,7 @@ def _collect(eng, action, weights, root_value):
     return got
 
 
-ENGINES = [1, 2, 3, 4, 5, 6, 7]  # MZ_ENGINE_STEPWISE, _FUSED (best available), _FUSED_CTA, _GROUP, _LANE, _LANE2, _RESIDENT
+ENGINES = [1, 2, 3, 4, 5, 6, 7, 8]  # MZ_ENGINE_STEPWISE, _FUSED (best available), _FUSED_CTA, _GROUP, _LANE, _LANE2, _RESIDENT, _FUSED_WARP
 
 
 def _fused_or_skip(eng, engine_id, run):
@@ -156,6 +156,40 @@ def test_headline_size_invariants_and_sampled_rows(c_oracle, engine_id):
     for lo in (0, 1777, 4064):
         want = c_oracle.search(nets, key, obs=obs[lo:lo + 32], global_batch=B, batch_offset=lo, **cfg)
         assert_same_search({k: v[lo:lo + 32] for k, v in got.items() if k in OUT_FIELDS}, want)
+
+
+@pytest.mark.parametrize("lanes,producers", [("8", "2"), ("16", "2"), ("8", "0"), ("16", "3")])
+@pytest.mark.parametrize("A,S,B,NS,max_depth,table_depth", [(2, 10, 301, 50, 0, None), (4, 10, 37, 40, 0, None),
+                                                            (3, 10, 129, 30, 5, None), (2, 5, 64, 24, 0, "2"),
+                                                            (4, 10, 200, 33, 0, "0")])
+def test_warp_engine_variants(c_oracle, monkeypatch, lanes, producers, A, S, B, NS, max_depth, table_depth):
+    """The warp-autonomous engine (mz_warp.cuh) in both widths (8 / 16 lanes per tree), on every compiled shape
+    variant, with ragged batches (surplus lane groups shadow the last tree), invalid actions at the root, a depth
+    limit, and with the pre-computed tie-break table cut short (MZ_GROUP_K: the in-loop threefry path takes over at
+    depth K; K = 0: no table at all), with the noise produced inside the kernel by dedicated warps (ring of
+    mbarrier-guarded slots) or by the pre-pass kernel (producers = 0) — bit-identical to the C restatement."""
+    monkeypatch.setenv("MZ_WARP_LANES", lanes)
+    monkeypatch.setenv("MZ_WARP_PRODUCERS", producers)
+    if table_depth is not None:
+        monkeypatch.setenv("MZ_GROUP_K", table_depth)
+    rng = np.random.default_rng(300 + A + S)
+    nets = make_nets(rng, 5, 8, A, 2 * S + 1, bias_scale=0.05)
+    obs = rng.standard_normal((B, 5)).astype(np.float32)
+    invalid = (rng.random((B, A)) < 0.25).astype(np.uint8) if A > 2 else None
+    if invalid is not None:
+        invalid[:, 0] = 0
+    key = np.array([9, 4000 + A], np.uint32)
+    cfg = dict(policy=0, qtransform=0, num_simulations=NS, support_size=S)
+    if max_depth:
+        cfg["max_depth"] = max_depth
+    want = c_oracle.search(nets, key, obs=obs, invalid=invalid, **cfg)
+    eng = _engine(nets, B, cfg, NS)
+    out = eng.search(key, obs=torch.from_numpy(obs).cuda(), invalid_actions=invalid, engine=8, **_search_kwargs(cfg))
+    got = _collect(eng, *out)
+    assert_same_search(got, want)
+    assert np.array_equal(got["sim_depth"], want["sim_depth"])
+    if not max_depth:  # a depth limit re-expands existing nodes: the A.8 invariants assume the default
+        check_tree_invariants(got, NS)
 
 
 @pytest.mark.parametrize("policy,qt,A,E,H,B,NS", [(0, 0, 4, 64, (64,), 64, 16), (1, 1, 18, 64, (64, 32), 24, 12),
