@@ -189,6 +189,32 @@ __device__ __forceinline__ void w_minmax(float (&v)[N_], bool enabled) {
   }
 }
 
+// The same normalisation dealt out over the lanes of a tree: every lane finds min / max of the raw row (shared memory
+// at `raw`), lane k divides element k, the quotients meet in `tmp` and every lane reloads the row — one division per
+// lane instead of N_ (identical operations per element).
+template <int N_>
+__device__ __forceinline__ void w_minmax_dist(const float* raw, float* tmp, int l, bool enabled, float (&v)[N_]) {
+  static_assert((N_ & (N_ - 1)) == 0, "power-of-two row");
+  w_load<N_>(raw, v);
+  if (!enabled) return;
+  float lo = v[0], hi = v[0];
+#pragma unroll
+  for (int k = 1; k < N_; ++k) {
+    lo = fminf(lo, v[k]);
+    hi = fmaxf(hi, v[k]);
+  }
+  float scale = MZ_SUB(hi, lo);
+  if (scale < 1e-5f) scale = MZ_ADD(scale, 1e-5f);
+  const int k = l & (N_ - 1);
+  const float num = MZ_SUB(raw[k], lo);
+  bool bad = !((__float_as_uint(scale) - 0x30800000u) < 0x1E800000u);
+  float qv = w_div_nn(num, scale, true, bad);
+  if (bad) qv = MZ_DIV(num, scale);
+  tmp[k] = qv;
+  __syncwarp();
+  w_load<N_>(tmp, v);
+}
+
 // Both categorical heads of one tree (muax/utils.py:94-102 on softmax(logits)): even lanes take the reward head
 // (logits at sc + sO1 + E), odd lanes the value head (sc + sO2); returns this lane's head scalar.
 template <int A, int E, int H, int S, int G>
@@ -303,14 +329,13 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
     tma_bulk_g2s(w, a.packed, (uint32_t)(round_up(net.packed_floats, 4) * 4), &wbar);
   }
   for (int n = tid; n < NS + 2; n += blockDim.x) pbc[n] = pbc_explore((float)n, a.p.pb_c_init, a.p.pb_c_base);
-  {
-    uint32_t* ub = reinterpret_cast<uint32_t*>(blocks);
-    for (int i = tid; i < trees * L.stride; i += blockDim.x) {
-      const int o = i % L.stride;
+  for (int tr = warp; tr < trees; tr += nwarps) {  // a warp per tree: no per-element division
+    uint32_t* ub = reinterpret_cast<uint32_t*>(blocks + (size_t)tr * L.stride);
+    for (int o = lane; o < L.stride; o += 32) {
       uint32_t v = 0u;
       if (o >= L.childs && o < L.raw && ((o - L.childs) & 3) == 0) v = kNoChild << 16;
       if (o < L.childs && (o & 3) == 3) v = 0xFFFFFFFFu;
-      ub[i] = v;
+      ub[o] = v;
     }
   }
   const bool searcher = warp < SW;
@@ -578,8 +603,7 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
       w_bias_act_store<U>(wq + W::D2 + H * 32, l, acc, false, 0, sc + W::sO1);
     }
     __syncwarp();
-    w_load<E>(sc + W::sO1, x);
-    w_minmax<E>(x, net.dyn_minmax != 0);
+    w_minmax_dist<E>(sc + W::sO1, sc + W::sE, l, net.dyn_minmax != 0, x);
     w_prediction<A, E, H, S, G>(wq, sc, l, x, act_kind);
     const float hs = w_heads<A, E, H, S, G>(sc, l);
     const float reward = __shfl_sync(0xffffffffu, hs, lane & ~(kWG - 1));
