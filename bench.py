@@ -292,7 +292,9 @@ def run_ours(args, wl, name):
                        "wall_s_incl_flush": wall},
             "e2e": {"value": e2e, "unit": "sims/s", "h2d_bytes_per_step": int(obs_host.nbytes),
                     "d2h_bytes_per_step": int(B * (4 + 4 * A + 4)), "ms_per_step": host_total_ms / args.steps,
-                    "api": "mz_search_host (host buffers -> pinned -> H2D -> search -> D2H -> sync)"},
+                    "api": "mz_search_host (host buffers -> pinned staging -> the search kernel reads the observations and "
+                           "writes action / action_weights / root_value over PCIe in place (mapped pinned memory; "
+                           "copy-engine H2D for observation batches > 256 KB) -> stream sync -> caller's buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,

@@ -626,7 +626,7 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
       root_emb = h->root_emb;
     }
     if (root_value_out != nullptr)
-      MZ_CUDA(cudaMemcpyAsync(root_value_out, root_value, sizeof(float) * h->cfg.batch, cudaMemcpyDeviceToDevice,
+      MZ_CUDA(cudaMemcpyAsync(root_value_out, root_value, sizeof(float) * h->cfg.batch, cudaMemcpyDefault,
                               stream));
     if (launch_begin(h, root_logits, root_value, root_emb, invalid, noise, stream)) return 1;
     if (run_stepwise(h, stream)) return 1;
@@ -859,8 +859,15 @@ int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_h
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t B = h->cfg.batch, BA = B * h->cfg.num_actions, BO = B * h->cfg.obs_dim;
+  // Zero-copy host I/O: the pinned staging buffers are mapped into the device's address space (unified addressing),
+  // so the kernels write action / action_weights / root_value straight into them — no D2H copy commands — and small
+  // observation batches are read in place by the search kernel's prologue instead of an H2D copy (four copy commands
+  // of ~7 us each were 10 % of an act at the headline shapes).  Large observation batches still go through the copy
+  // engine.  MZ_HOST_COPIES=1 restores the explicit copies.
+  static const bool explicit_copies = getenv("MZ_HOST_COPIES") != nullptr && atoi(getenv("MZ_HOST_COPIES")) != 0;
+  const bool obs_in_place = !explicit_copies && BO * sizeof(float) <= (size_t)256 * 1024;
   std::memcpy(h->h_obs, obs_host, BO * sizeof(float));
-  MZ_CUDA(cudaMemcpyAsync(h->d_obs, h->h_obs, BO * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (!obs_in_place) MZ_CUDA(cudaMemcpyAsync(h->d_obs, h->h_obs, BO * sizeof(float), cudaMemcpyHostToDevice, s));
   if (invalid_host != nullptr) {
     std::memcpy(h->h_invalid, invalid_host, BA);
     MZ_CUDA(cudaMemcpyAsync(h->d_invalid, h->h_invalid, BA, cudaMemcpyHostToDevice, s));
@@ -869,12 +876,17 @@ int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_h
     std::memcpy(h->h_noise, noise_host, BA * sizeof(float));
     MZ_CUDA(cudaMemcpyAsync(h->d_noise, h->h_noise, BA * sizeof(float), cudaMemcpyHostToDevice, s));
   }
-  if (search_device(h, h->d_obs, nullptr, nullptr, nullptr, invalid_host ? h->d_invalid : nullptr,
-                    noise_host ? h->d_noise : nullptr, args, h->d_action_out, h->d_weights_out, h->d_value_out, s))
+  if (search_device(h, obs_in_place ? h->h_obs : h->d_obs, nullptr, nullptr, nullptr,
+                    invalid_host ? h->d_invalid : nullptr, noise_host ? h->d_noise : nullptr, args,
+                    explicit_copies ? h->d_action_out : h->h_action_out,
+                    explicit_copies ? h->d_weights_out : h->h_weights_out,
+                    explicit_copies ? h->d_value_out : h->h_value_out, s))
     return 1;
-  MZ_CUDA(cudaMemcpyAsync(h->h_action_out, h->d_action_out, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  MZ_CUDA(cudaMemcpyAsync(h->h_weights_out, h->d_weights_out, BA * sizeof(float), cudaMemcpyDeviceToHost, s));
-  MZ_CUDA(cudaMemcpyAsync(h->h_value_out, h->d_value_out, B * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (explicit_copies) {
+    MZ_CUDA(cudaMemcpyAsync(h->h_action_out, h->d_action_out, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    MZ_CUDA(cudaMemcpyAsync(h->h_weights_out, h->d_weights_out, BA * sizeof(float), cudaMemcpyDeviceToHost, s));
+    MZ_CUDA(cudaMemcpyAsync(h->h_value_out, h->d_value_out, B * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
   MZ_CUDA(cudaStreamSynchronize(s));
   std::memcpy(action_out_host, h->h_action_out, B * sizeof(int32_t));
   if (action_weights_out_host) std::memcpy(action_weights_out_host, h->h_weights_out, BA * sizeof(float));
