@@ -7,8 +7,9 @@ from .policy import (GumbelMuZeroPolicy, MuZeroPolicy, Policy, PolicyOutput, Rec
                      qtransform_completed_by_mix_value)
 from .search import SearchEngine  # noqa: F401
 from .actor import BatchedPNStep, CartPoleVec, TrajectoryStore, Transitions, VectorActor  # noqa: F401
+from .train import fit, test  # noqa: F401
 
 __all__ = ["MuZero", "MZNetwork", "MZNetworkParams", "create_muzero_network", "Policy", "MuZeroPolicy",
            "GumbelMuZeroPolicy", "StochasticMuZeroPolicy", "PolicyOutput", "RootFnOutput", "RecurrentFnOutput",
-           "SearchEngine", "BatchedPNStep", "TrajectoryStore", "Transitions", "VectorActor", "CartPoleVec", "nn", "random",
+           "SearchEngine", "fit", "test", "BatchedPNStep", "TrajectoryStore", "Transitions", "VectorActor", "CartPoleVec", "nn", "random",
            "utils"]
