@@ -715,51 +715,48 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
     }
   }
 
+    // ---- dump: every warp unpacks its own trees into the mctx SoA arrays as soon as it is done (no CTA barrier:
+    // the act ends with its slowest warp, the others have written their trees by then)
+    if (a.dump_tree) {
+      __syncwarp();
+      const Tree& o = a.out;
+      for (int tt = 0; tt < kWT; ++tt) {
+        const int tr = warp * kWT + tt;
+        if (row0 + tr >= a.B) break;
+        const float* tb = blocks + (size_t)tr * L.stride;
+        for (int n = lane; n < N; n += 32) {
+          const float4 nd = reinterpret_cast<const float4*>(tb + L.nodes)[n];
+          const size_t g = (size_t)(row0 + tr) * o.N + n;
+          const uint32_t pa = __float_as_uint(nd.w);
+          o.node_visits[g] = __float_as_int(nd.x);
+          o.parents[g] = pa == 0xFFFFFFFFu ? -1 : (int)(pa >> 8);
+          o.action_from_parent[g] = pa == 0xFFFFFFFFu ? -1 : (int)(pa & 0xFFu);
+          o.raw_values[g] = (tb + L.raw)[n];
+          o.node_values[g] = nd.y;
+        }
+        for (int k = lane; k < N * A; k += 32) {
+          const float4 c = reinterpret_cast<const float4*>(tb + L.childs)[k];
+          const size_t g = (size_t)(row0 + tr) * o.N * A + k;
+          const uint32_t cx = __float_as_uint(c.x);
+          const bool has = (cx >> 16) != kNoChild;
+          o.children_index[g] = has ? (int)(cx >> 16) : -1;
+          o.children_visits[g] = (int)(cx & 0xFFFFu);
+          o.children_prior_logits[g] = (tb + L.logits)[k];
+          o.children_prior_probs[g] = c.y;
+          o.children_values[g] = c.z;
+          o.children_rewards[g] = c.w;
+          o.children_discounts[g] = has ? gamma : 0.0f;
+        }
+        for (int k = lane; k < N * E; k += 32)
+          o.embeddings[(size_t)(row0 + tr) * o.N * E + k] = (tb + L.emb)[k];
+        if (lane < A) {
+          const float* rt = tb + L.root;
+          o.root_noise[(size_t)(row0 + tr) * A + lane] = rt[lane];
+          o.root_invalid[(size_t)(row0 + tr) * A + lane] = rt[A + lane] != 0.0f ? 1 : 0;
+        }
+      }
+    }
   }  // search warps
-
-  // ---- dump: unpack the records into the mctx SoA arrays
-  if (a.dump_tree) {
-    __syncthreads();
-    const Tree& o = a.out;
-    const int live_trees = max(0, min(trees, a.B - row0));
-    for (int i = tid; i < live_trees * N; i += blockDim.x) {
-      const int tr = i / N, n = i - tr * N;
-      const float* tb = blocks + (size_t)tr * L.stride;
-      const float4 nd = reinterpret_cast<const float4*>(tb + L.nodes)[n];
-      const size_t g = (size_t)(row0 + tr) * o.N + n;
-      const uint32_t pa = __float_as_uint(nd.w);
-      o.node_visits[g] = __float_as_int(nd.x);
-      o.parents[g] = pa == 0xFFFFFFFFu ? -1 : (int)(pa >> 8);
-      o.action_from_parent[g] = pa == 0xFFFFFFFFu ? -1 : (int)(pa & 0xFFu);
-      o.raw_values[g] = (tb + L.raw)[n];
-      o.node_values[g] = nd.y;
-    }
-    for (int i = tid; i < live_trees * N * A; i += blockDim.x) {
-      const int tr = i / (N * A), k = i - tr * (N * A);
-      const float* tb = blocks + (size_t)tr * L.stride;
-      const float4 c = reinterpret_cast<const float4*>(tb + L.childs)[k];
-      const size_t g = (size_t)(row0 + tr) * o.N * A + k;
-      const uint32_t cx = __float_as_uint(c.x);
-      const bool has = (cx >> 16) != kNoChild;
-      o.children_index[g] = has ? (int)(cx >> 16) : -1;
-      o.children_visits[g] = (int)(cx & 0xFFFFu);
-      o.children_prior_logits[g] = (tb + L.logits)[k];
-      o.children_prior_probs[g] = c.y;
-      o.children_values[g] = c.z;
-      o.children_rewards[g] = c.w;
-      o.children_discounts[g] = has ? gamma : 0.0f;
-    }
-    for (int i = tid; i < live_trees * N * E; i += blockDim.x) {
-      const int tr = i / (N * E), k = i - tr * (N * E);
-      o.embeddings[(size_t)(row0 + tr) * o.N * E + k] = (blocks + (size_t)tr * L.stride + L.emb)[k];
-    }
-    for (int i = tid; i < live_trees * A; i += blockDim.x) {
-      const int tr = i / A, x = i - tr * A;
-      const float* rt = blocks + (size_t)tr * L.stride + L.root;
-      o.root_noise[(size_t)(row0 + tr) * A + x] = rt[x];
-      o.root_invalid[(size_t)(row0 + tr) * A + x] = rt[A + x] != 0.0f ? 1 : 0;
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------- host side
