@@ -205,11 +205,13 @@ def run_ours(args, wl, name):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
     from muax_b200.sharded import ShardedSearch
     kw_local = {k: v for k, v in kw.items() if k not in ("global_batch", "batch_offset")}
-    sharded = ShardedSearch(lambda key, obs, **k2: eng.search(key, obs=obs, **k2), GB, A, writes_into_out=True)
+    peer = {"auto": None, "on": True, "off": False}[os.environ.get("MZ_PEER_STORES", "off")]
+    sharded = ShardedSearch(eng.search, GB, A, writes_into_out=True, peer_stores=peer)
 
     def step_device(i):
         # rows [rank*B, (rank+1)*B) of the global batch; with world > 1 this ends with the one all-gather of
-        # (action_weights, root_value, action) for the shared replay buffer (NCCL over NVLink)
+        # (action_weights, root_value, action) for the shared replay buffer — done by the search kernel's own NVLink
+        # peer stores + a cross-rank barrier when symmetric memory is available, else one NCCL all-gather
         key = np.array([0, i], np.uint32)
         return sharded.act(key, obs_dev, **kw_local)
 
@@ -287,6 +289,7 @@ def run_ours(args, wl, name):
             "config": {"workload": name, "batch_per_gpu": B, "global_batch": GB, "num_simulations": NS,
                        "num_actions": A, "embed_dim": wl["E"], "policy": "muzero" if wl["policy"] == 0 else "gumbel",
                        "engine": args.engine, "mean_path_depth": depth, "parallelism": f"dp{world}",
+                       "exchange": sharded.exchange,
                        "l2": "256 MB buffer written between timed steps (outside the CUDA-event window)",
                        "timing": "CUDA events per step on the launching stream, summed, max over ranks",
                        "wall_s_incl_flush": wall},

@@ -144,8 +144,17 @@ int mz_search(mz_handle* h, const float* obs_dev, const float* root_logits_dev, 
               const mz_search_args* args, int32_t* action_out_dev, float* action_weights_out_dev,
               float* root_value_out_dev, void* stream);
 
+/* Multi-GPU env sharding (the reference has no counterpart — its act is single-process): the next
+ * mz_search calls store action / action_weights / root_value not only at the given output pointers but also at
+ * (pointer + byte_deltas[i]) for i < n — the same slots of the peer GPUs' gather buffers, mapped into this process
+ * (CUDA IPC / torch symmetric memory) — so the per-act all-gather is done by the search kernel's own NVLink stores.
+ * Only the warp engine honours it (mz_search fails otherwise); n = 0 switches it off.  The caller orders the peers'
+ * reads after the stores (a cross-rank barrier after the kernel). */
+int mz_set_peer_outputs(mz_handle* h, int32_t n, const int64_t* byte_deltas);
+
 /* Same call with HOST buffers (what `MuZero.act` sees: numpy in, numpy out — model.py:160-174): stages
- * through pinned memory, copies H2D, searches, copies D2H and synchronises the stream. */
+ * through mapped pinned memory (read / written in place by the kernels; copy-engine H2D for large observation
+ * batches), searches and synchronises the stream. */
 int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_host, const float* noise_host,
                    const mz_search_args* args, int32_t* action_out_host, float* action_weights_out_host,
                    float* root_value_out_host, void* stream);

@@ -63,6 +63,10 @@ struct LaneArgs {
   float* root_value_out;
   int32_t B, N, dump_tree;
   int32_t walkers;  // lane2: warps that walk trees (select / expand / backup); 0 = all of them
+  // warp engine: action / action_weights / root_value are also stored at (pointer + peer_delta[i]) — the same slots of
+  // the peer GPUs' gather buffers (NVLink peer stores; muax_b200/sharded.py)
+  int32_t n_peers;
+  int64_t peer_delta[7];
 };
 
 __global__ void lane_pack_kernel(const float* __restrict__ raw, float* __restrict__ packed, LPackDesc d) {

@@ -433,7 +433,11 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
     const float rv = __shfl_sync(0xffffffffu, hs, (lane & ~(kWG - 1)) + 1);
     const float* bufP = sc + W::sO2 + F4;
     // policy prologue (A.2) + node 0: every lane of the tree computes and stores the same values
-    if (live && l == 0 && a.root_value_out != nullptr) a.root_value_out[b] = rv;
+    if (live && l == 0 && a.root_value_out != nullptr) {
+      a.root_value_out[b] = rv;
+      for (int q = 0; q < a.n_peers; ++q)
+        *reinterpret_cast<float*>(reinterpret_cast<char*>(a.root_value_out + b) + a.peer_delta[q]) = rv;
+    }
     float mx = -mz_inf();
 #pragma unroll
     for (int x = 0; x < A; ++x) mx = fmaxf(mx, bufP[x]);
@@ -712,6 +716,12 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
 #pragma unroll
       for (int x = 0; x < A; ++x) a.weights_out[(size_t)b * A + x] = wgt[x];
       a.action_out[b] = best;
+      for (int q = 0; q < a.n_peers; ++q) {  // the all-gather of the sharded act, done by the kernel itself
+        char* wp = reinterpret_cast<char*>(a.weights_out + (size_t)b * A) + a.peer_delta[q];
+#pragma unroll
+        for (int x = 0; x < A; ++x) reinterpret_cast<float*>(wp)[x] = wgt[x];
+        *reinterpret_cast<int32_t*>(reinterpret_cast<char*>(a.action_out + b) + a.peer_delta[q]) = best;
+      }
     }
   }
 
@@ -839,7 +849,8 @@ inline bool warp_supported(const WarpState& st, const LaneState& ls, const Searc
 
 inline int warp_launch(WarpState& st, LaneState& ls, const Tree& out, const SearchParams& p, const float* obs,
                        const uint8_t* invalid, const float* noise, int32_t* action_out, float* weights_out,
-                       float* root_value_out, cudaStream_t stream, int64_t* launches, std::string* err) {
+                       float* root_value_out, const std::vector<int64_t>& peers, cudaStream_t stream,
+                       int64_t* launches, std::string* err) {
   const int B = out.B, NS = p.num_simulations, N = NS + 1, A = ls.net.A;
   LaneArgs a{};
   a.net = ls.net;
@@ -854,6 +865,8 @@ inline int warp_launch(WarpState& st, LaneState& ls, const Tree& out, const Sear
   a.root_value_out = root_value_out;
   a.B = B;
   a.N = N;
+  a.n_peers = (int)std::min<size_t>(peers.size(), 7);
+  for (int i = 0; i < a.n_peers; ++i) a.peer_delta[i] = peers[i];
   a.dump_tree = getenv("MZ_FUSED_NO_DUMP") ? 0 : 1;
   a.K = std::min(16, kGNoiseFloats / A);
   if (const char* k = getenv("MZ_GROUP_K")) a.K = std::max(0, std::min(a.K, atoi(k)));

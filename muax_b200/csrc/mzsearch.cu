@@ -334,6 +334,7 @@ struct mz_handle {
   mz::LaneState lanes;
   mz::Lane2State lane2;
   mz::WarpState warpeng;
+  std::vector<int64_t> peer_deltas;  // mz_set_peer_outputs
   mz::ResidentState resident;
 };
 
@@ -576,6 +577,9 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   if (engine == MZ_ENGINE_FUSED_LANE) engine = kLane;
   if (engine == MZ_ENGINE_FUSED_LANE2) engine = kLane2;
   if (engine == MZ_ENGINE_FUSED_WARP) engine = kWarp;
+  if (!h->peer_deltas.empty() && engine != kWarp)
+    return fail("peer outputs (mz_set_peer_outputs) are written by the warp engine only; this configuration runs on "
+                "another engine — clear them and exchange the outputs with a collective");
   if (engine == MZ_ENGINE_RESIDENT) {
     if (!resident_ok) return fail("the resident engine does not support this configuration (see DESIGN.md)");
     if (obs != nullptr && h->cfg.obs_dim <= 0)
@@ -598,7 +602,7 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
     std::string err;
     if (engine == kWarp) {
       if (warp_launch(h->warpeng, h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
-                      root_value_out, stream, &h->launches, &err))
+                      root_value_out, h->peer_deltas, stream, &h->launches, &err))
         return fail(err);
     } else if (engine == kLane2) {
       if (lane2_launch(h->lane2, h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
@@ -848,6 +852,14 @@ int mz_search(mz_handle* h, const float* obs_dev, const float* root_logits_dev, 
   if (h == nullptr) return mz::fail("mz_search: NULL handle");
   return mz::search_device(h, obs_dev, root_logits_dev, root_value_dev, root_emb_dev, invalid_dev, noise_dev, args,
                            action_out_dev, action_weights_out_dev, root_value_out_dev, (cudaStream_t)stream);
+}
+
+int mz_set_peer_outputs(mz_handle* h, int32_t n, const int64_t* byte_deltas) {
+  using namespace mz;
+  if (h == nullptr || n < 0 || n > 7 || (n > 0 && byte_deltas == nullptr))
+    return fail("mz_set_peer_outputs: expected 0..7 byte offsets");
+  h->peer_deltas.assign(byte_deltas, byte_deltas + n);
+  return 0;
 }
 
 int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_host, const float* noise_host,

@@ -114,6 +114,13 @@ class SearchEngine:
                 rc = self.lib.mz_set_weights(self._h, ctypes.c_void_p(blob.ctypes.data), blob.size, 0, stream)
         _lib.check(rc, "mz_set_weights")
 
+    def set_peer_outputs(self, byte_deltas):
+        """The next searches also store their outputs at (output pointer + delta) for every delta: the same slots of
+        the peer GPUs' gather buffers (muax_b200/sharded.py).  Empty list = off.  Warp engine only."""
+        deltas = [int(d) for d in byte_deltas]
+        arr = (ctypes.c_int64 * max(len(deltas), 1))(*deltas)
+        _lib.check(self.lib.mz_set_peer_outputs(self._h, len(deltas), arr), "mz_set_peer_outputs")
+
     # ------------------------------------------------------------------ arguments
     def make_args(self, rng_key, *, policy=_lib.POLICY_MUZERO, qtransform=None, num_simulations=5, temperature=1.0,
                   max_depth=None, dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25, pb_c_base=19652,

@@ -37,7 +37,7 @@ class ShardedSearch:
     search_fn(rng_key, obs_local, global_batch=..., batch_offset=..., **kw) -> (action, weights, value) tensors;
     with a `SearchEngine` pass `engine.search` (observations via `obs=`)."""
 
-    def __init__(self, search_fn, global_batch, num_actions, group=None, writes_into_out=False):
+    def __init__(self, search_fn, global_batch, num_actions, group=None, writes_into_out=False, peer_stores=False):
         """writes_into_out: `search_fn` accepts `out=(action, weights, value)` and writes its results there
         (SearchEngine.search does).  With even shards the three outputs are then views of ONE flat send buffer, so
         the step is: search kernels -> one all-gather -> three strided copies, no packing kernels."""
@@ -52,6 +52,15 @@ class ShardedSearch:
         self.offset, self.count = shard_bounds(self.global_batch, self.world, self.rank)
         self.max_count = shard_bounds(self.global_batch, self.world, 0)[1]
         self._gather_buf = None
+        # peer_stores: the search kernel writes its outputs straight into every rank's gather buffer over NVLink
+        # (torch symmetric memory + SearchEngine.set_peer_outputs) and the step ends with a cross-rank barrier instead
+        # of an NCCL all-gather.  Opt-in: measured on 2 x B200 at the headline shapes the barrier kernel costs what the
+        # 64 KB all-gather costs (0.336 vs 0.324 ms per act, profiles/r01_bench_n2_peer_*.json).  True = require it,
+        # None = try it and fall back to NCCL, False (default) = NCCL.
+        self.peer_stores = peer_stores
+        self.exchange = "none" if self.world == 1 else "nccl all-gather"
+        self._peer = None
+        self._step = 0
 
     def local_rows(self, global_tensor):
         return global_tensor[self.offset:self.offset + self.count]
@@ -79,10 +88,65 @@ class ShardedSearch:
             parts.append(self._gather_buf[r * self.max_count:r * self.max_count + cnt])
         return unpack_outputs(torch.cat(parts, dim=0))
 
+    def _setup_peer(self, dev, row):
+        """Two symmetric gather buffers (alternating per act, so that a fast rank's stores of act t+1 never land in a
+        buffer a slow rank still reads from act t) + the byte offsets from this rank's buffer to each peer's."""
+        engine = getattr(self.search_fn, "__self__", None)
+        if self.peer_stores is False or engine is None or not hasattr(engine, "set_peer_outputs") or self.world > 8:
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            bufs, hdls, deltas = [], [], []
+            for _ in range(2):
+                buf = symm.empty(self.world * row, dtype=torch.float32, device=dev)
+                hdl = symm.rendezvous(buf, group)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                bufs.append(buf)
+                hdls.append(hdl)
+                deltas.append([ptrs[q] - ptrs[self.rank] for q in range(self.world) if q != self.rank])
+            self._peer = (engine, bufs, hdls, deltas)
+            self.exchange = "peer stores from the search kernel + symmetric-memory barrier"
+            return True
+        except Exception as e:  # no P2P / symmetric memory on this system: keep the NCCL path, say so
+            if self.peer_stores is True:
+                raise
+            self.exchange = f"nccl all-gather (peer stores unavailable: {type(e).__name__})"
+            self.peer_stores = False
+            return False
+
+    def _act_peer(self, rng_key, obs_local, row, **kw):
+        n, A, W = self.count, self.A, self.world
+        engine, bufs, hdls, deltas = self._peer
+        k = self._step & 1
+        self._step += 1
+        mine = bufs[k][self.rank * row:(self.rank + 1) * row]
+        out = (mine[n * A + n:].view(torch.int32), mine[:n * A].view(n, A), mine[n * A:n * A + n])
+        engine.set_peer_outputs(deltas[k])
+        try:
+            self.search_fn(rng_key, obs_local, global_batch=self.global_batch, batch_offset=self.offset, out=out, **kw)
+        finally:
+            engine.set_peer_outputs([])
+        hdls[k].barrier(channel=0)  # every rank's kernel (and its NVLink stores) is complete past this point
+        r = bufs[k].view(W, row)
+        weights = r[:, :n * A].reshape(W * n, A)
+        value = r[:, n * A:n * A + n].reshape(W * n)
+        action = r[:, n * A + n:].view(torch.int32).reshape(W * n)
+        return action, weights, value
+
     def _act_flat(self, rng_key, obs_local, **kw):
         n, A, W = self.count, self.A, self.world
         row = n * (A + 2)  # floats per rank: weights [n, A] | value [n] | action [n] (int32 bits)
         dev = obs_local.device
+        if self.peer_stores is not False and dev.type == "cuda":
+            if self._peer is not None or self._setup_peer(dev, row):
+                try:
+                    return self._act_peer(rng_key, obs_local, row, **kw)
+                except RuntimeError as e:
+                    if self.peer_stores is True or "warp engine only" not in str(e):
+                        raise
+                    self.peer_stores, self._peer = False, None  # this configuration runs on another engine
+                    self.exchange = "nccl all-gather (the configuration does not run on the warp engine)"
         if self._send is None or self._send.device != dev:
             self._send = torch.empty(row, dtype=torch.float32, device=dev)
             self._recv = torch.empty(W * row, dtype=torch.float32, device=dev)
