@@ -75,8 +75,9 @@ class DevicePNStep:
         trans = Transitions(obs=self._obs[rows, slot], a=torch.gather(self._a, 1, slot), r=torch.gather(self._r, 1, slot),
                             done=~boot, Rn=Rn, v=v_slot, pi=self._pi[rows, slot], w=w)
         popped = steady[:, 0].to(torch.int64)
-        self._head = torch.where(done, torch.zeros_like(self._head), (self._head + popped) % C)
-        self._len = torch.where(done, torch.zeros_like(self._len), self._len - popped)
+        # in place: the step may be replayed from a CUDA graph, which sees the state through fixed addresses
+        self._head.copy_(torch.where(done, torch.zeros_like(self._head), (self._head + popped) % C))
+        self._len.copy_(torch.where(done, torch.zeros_like(self._len), self._len - popped))
         return trans, mask
 
 
@@ -101,7 +102,7 @@ class CartPoleVecTorch:
         return torch.rand(self.batch, 4, dtype=torch.float64, device=self.device, generator=self.gen) * 0.1 - 0.05
 
     def reset(self):
-        self.state = self._fresh()
+        self.state.copy_(self._fresh())
         self.t.zero_()
         return self.state.to(torch.float32)
 
@@ -118,17 +119,22 @@ class CartPoleVecTorch:
         self.t += 1
         terminated = (state[:, 0].abs() > self.X_LIMIT) | (state[:, 2].abs() > self.THETA_LIMIT)
         done = terminated | (self.t >= self.MAX_STEPS)
-        self.state = torch.where(done[:, None], self._fresh(), state)
-        self.t = torch.where(done, torch.zeros_like(self.t), self.t)
+        self.state.copy_(torch.where(done[:, None], self._fresh(), state))  # in place (CUDA-graph replay)
+        self.t.copy_(torch.where(done, torch.zeros_like(self.t), self.t))
         reward = torch.ones(self.batch, dtype=torch.float64, device=self.device)
         return self.state.to(torch.float32), reward, done
 
 
 class DeviceActor:
-    """actor.VectorActor with everything but the finished episodes resident on the GPU."""
+    """actor.VectorActor with everything but the finished episodes resident on the GPU.
+
+    Per step: the search (one kernel, written into fixed output buffers), then environment step + tracer + episode
+    scatter — ~90 small fixed-shape torch kernels that are launch-bound next to a 0.3 ms search, so on CUDA they are
+    captured once into a **CUDA graph** and replayed (`use_graph`; all state is updated in place) — then ONE tiny D2H
+    (which environments ended).  The tensors `step` returns are the fixed buffers: valid until the next step."""
 
     def __init__(self, model, env, store, n=10, gamma=0.997, alpha=0.5, k_steps=5, num_simulations=50,
-                 temperature=1.0, act_kwargs=None, max_episode_steps=None):
+                 temperature=1.0, act_kwargs=None, max_episode_steps=None, use_graph=None):
         self.model, self.env, self.store = model, env, store
         self.device = env.device
         self.tracer = DevicePNStep(env.batch, n, gamma, alpha, device=self.device)
@@ -136,15 +142,22 @@ class DeviceActor:
         self.act_kwargs = dict(act_kwargs or {})
         self.L = int(max_episode_steps or getattr(env, "MAX_STEPS", 1000))
         self._episode = None  # Transitions of [batch, L + 1, ...] tensors; column L swallows masked-off writes
-        self._ep_len = torch.zeros(env.batch, dtype=torch.int64, device=self.device)
-        self._rows = torch.arange(env.batch, device=self.device)
-        self.obs = env.reset()
+        B = env.batch
+        self._ep_len = torch.zeros(B, dtype=torch.int64, device=self.device)
+        self._rows = torch.arange(B, device=self.device)
+        self.obs = env.reset().clone()
+        self._out = (torch.zeros(B, dtype=torch.int32, device=self.device),
+                     torch.zeros(B, env.num_actions, dtype=torch.float32, device=self.device),
+                     torch.zeros(B, dtype=torch.float32, device=self.device))
+        self._done = torch.zeros(B, dtype=torch.bool, device=self.device)
+        self.use_graph = (self.device.type == "cuda") if use_graph is None else bool(use_graph)
+        self._graph, self._eager_steps = None, 0
         self.env_steps = 0
         self.episodes = 0
 
-    def step(self, rng_key):
-        action, weights, value = self.model.act_device(rng_key, self.obs, num_simulations=self.num_simulations,
-                                                       temperature=self.temperature, **self.act_kwargs)
+    def _after_search(self):
+        """Environment step, tracer, scatter into the episodes in progress: fixed shapes, state updated in place."""
+        action, weights, value = self._out
         obs_next, r, done = self.env.step(action)
         trans, mask = self.tracer.add(self.obs, action, r, done, value, weights)
         B, C = mask.shape
@@ -158,8 +171,34 @@ class DeviceActor:
         rows = self._rows[:, None].expand(B, C)
         for dst, src in zip(self._episode, trans):
             dst[rows, pos] = src
-        self._ep_len = self._ep_len + mask.sum(1)
-        ended = torch.nonzero(done)[:, 0]  # the one host sync of the step
+        self._ep_len.add_(mask.sum(1))
+        self._done.copy_(done)
+        self.obs.copy_(obs_next)
+
+    def _capture(self):
+        graph = torch.cuda.CUDAGraph()
+        gen = getattr(self.env, "gen", None)
+        if gen is not None:
+            graph.register_generator_state(gen)  # the environment draws its reset states inside the graph
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(graph):
+            self._after_search()
+        return graph
+
+    def step(self, rng_key):
+        self.model.act_device(rng_key, self.obs, num_simulations=self.num_simulations, temperature=self.temperature,
+                              out=self._out, **self.act_kwargs)
+        if self._graph is not None:
+            self._graph.replay()
+        elif self.use_graph and self._eager_steps >= 2:  # two eager steps allocate the lazily-shaped buffers first
+            self._graph = self._capture()                # capture only records: nothing has run yet
+            self._graph.replay()
+        else:
+            self._after_search()
+            self._eager_steps += 1
+        action, weights, value = self._out
+        B = self.env.batch
+        ended = torch.nonzero(self._done)[:, 0]  # the one host sync of the step
         if len(ended):
             lengths = self._ep_len[ended].cpu().numpy()
             longest = int(lengths.max())
@@ -169,6 +208,5 @@ class DeviceActor:
                     self.store.add(Transitions(*(blk[j, :length] for blk in blocks)))
             self.episodes += len(lengths)
             self._ep_len[ended] = 0
-        self.obs = obs_next
         self.env_steps += B
-        return action, weights, value, done
+        return action, weights, value, self._done

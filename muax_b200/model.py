@@ -197,7 +197,8 @@ class MuZero:
 
     def act_device(self, rng_key, obs, num_simulations: int = 5, temperature: float = 1.0, **kw):
         """`act` for device-resident loops (muax_b200/actor_device.py): `obs` is a CUDA float32 tensor [B, ...];
-        returns CUDA tensors (action i32[B], action_weights f32[B,A], root_value f32[B]) without synchronising."""
+        returns CUDA tensors (action i32[B], action_weights f32[B,A], root_value f32[B]) without synchronising.
+        `out=(action, weights, root_value)`: preallocated tensors the search kernel writes into (native nets only)."""
         if not isinstance(obs, torch.Tensor) or not obs.is_cuda:
             raise ValueError("act_device expects a CUDA tensor; use act() for host observations")
         plan_output, root_value = self._plan(self._params, rng_key, obs.to(torch.float32), num_simulations=num_simulations,
@@ -209,6 +210,7 @@ class MuZero:
               **extra):  # muax/model.py:222-243
         if qtransform is None:  # model.py:230-231 forces this default for every policy class
             qtransform = _lib.QT_PARENT_AND_SIBLINGS
+        out = extra.pop("out", None)
         kwargs = dict(num_simulations=num_simulations, temperature=temperature, invalid_actions=invalid_actions,
                       max_depth=max_depth, qtransform=qtransform, dirichlet_fraction=dirichlet_fraction,
                       dirichlet_alpha=dirichlet_alpha, pb_c_init=pb_c_init, pb_c_base=pb_c_base, **extra)
@@ -227,11 +229,15 @@ class MuZero:
             engine = self._engine_for(obs2.shape[0], num_simulations, params)
             kw = self._policy._search_kwargs(kwargs)
             action, weights, root_value = engine.search(rng_key, obs=obs2, invalid_actions=invalid_actions,
-                                                        noise=extra.get("noise"), **kw)
+                                                        noise=extra.get("noise"), out=out, **kw)
             from .policy import PolicyOutput
             return PolicyOutput(action, weights, engine), root_value
         root = self._root_inference(params, rng_key, obs)
         plan_output = self._policy(params, rng_key, root, self._recurrent_inference, **kwargs)
+        if out is not None:  # callback path: results land in fresh tensors, copy them into the caller's buffers
+            out[0].copy_(plan_output.action)
+            out[1].copy_(plan_output.action_weights)
+            out[2].copy_(root.value)
         return plan_output, root.value
 
     def _root_inference(self, params, rng_key, obs):  # muax/model.py:251-263 (torch-callable networks)

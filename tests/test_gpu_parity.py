@@ -367,9 +367,11 @@ def test_vector_actor_on_the_gpu_search():
     assert batch.obs.shape == (32, 5, 4) and batch.pi.shape == (32, 5, 2) and np.all(batch.w >= 0)
 
 
-def test_device_actor_equals_numpy_actor_data_path():
-    """Device-resident acting loop (CartPoleVecTorch + DevicePNStep on the GPU): the episodes it stores must be what
-    the reference-pinned NumPy tracer produces from the same per-step (obs, a, r, done, v, pi) stream."""
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_device_actor_equals_numpy_actor_data_path(use_graph):
+    """Device-resident acting loop (CartPoleVecTorch + DevicePNStep on the GPU; eager, and with everything after the
+    search replayed from a CUDA graph): the episodes it stores must be what the reference-pinned NumPy tracer produces
+    from the same per-step (obs, a, r, done, v, pi) stream."""
     import muax_b200
     from muax_b200 import nn
     from muax_b200.actor import BatchedPNStep, TrajectoryStore
@@ -380,7 +382,7 @@ def test_device_actor_equals_numpy_actor_data_path():
     B = 128
     env = CartPoleVecTorch(B, seed=5)
     store = TrajectoryStore(100000, random_seed=0)
-    actor = DeviceActor(model, env, store, n=5, gamma=0.997, k_steps=1, num_simulations=8)
+    actor = DeviceActor(model, env, store, n=5, gamma=0.997, k_steps=1, num_simulations=8, use_graph=use_graph)
     ref = BatchedPNStep(B, 5, 0.997, 0.5)
     ref_eps, pending = [], [[] for _ in range(B)]
     for t in range(45):

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--num-simulations", type=int, default=50)
     ap.add_argument("--device-loop", action="store_true", help="tracer + environment on the GPU (actor_device.py)")
+    ap.add_argument("--no-graph", action="store_true", help="device loop without the CUDA graph (eager torch kernels)")
     ap.add_argument("--long-episodes", action="store_true",
                     help="no early termination: episodes run the full 500 steps, as with a trained CartPole agent "
                          "(random weights end ~10% of the environments every step)")
@@ -36,7 +37,8 @@ def main():
         import torch
         from muax_b200.actor_device import CartPoleVecTorch, DeviceActor
         env = CartPoleVecTorch(args.batch, seed=0, **lim)
-        actor = DeviceActor(model, env, store, n=10, gamma=0.997, k_steps=5, num_simulations=args.num_simulations)
+        actor = DeviceActor(model, env, store, n=10, gamma=0.997, k_steps=5, num_simulations=args.num_simulations,
+                            use_graph=not args.no_graph)
         for t in range(5):
             actor.step(muax_b200.random.PRNGKey(t))
         torch.cuda.synchronize()
