@@ -49,11 +49,13 @@ def fit(model, env, test_env=None, n_steps=10, gamma=0.997, alpha=0.5, buffer=No
         max_iterations=1000, steps_per_iteration=None, test_interval=10, num_test_episodes=None,
         max_training_steps=10000, num_simulations=50, k_steps=10, buffer_warm_up=128, num_trajectory=32,
         sample_per_trajectory=10, model_save_path=None, save_name="model_params", random_seed=42,
-        temperature_fn=_temperature_fn, num_update_per_episode=50, log=None):
+        temperature_fn=_temperature_fn, num_update_per_episode=50, log=None, actor_cls=VectorActor):
     """Fits `model` on the vector environment `env`.  Keyword names and defaults follow muax/train.py:26-52
     (`tracer=PNStep(n_steps, gamma, alpha)` is spelled out because the batched tracer is built per environment
     batch).  Returns `(model_path, history)`: the path of the best parameters seen in testing (None when nothing was
-    saved) and a list of per-iteration dicts {iteration, training_step, loss, episodes, env_steps, test_G, seconds}."""
+    saved) and a list of per-iteration dicts {iteration, training_step, loss, episodes, env_steps, test_G, seconds}.
+    `actor_cls=muax_b200.actor_device.DeviceActor` with a torch vector environment (`CartPoleVecTorch`) keeps the
+    acting phase on the GPU (search kernel + one CUDA graph per step)."""
     if env is None:
         raise ValueError("You must provide a vector `env` (gym is not a dependency of this package).")
     buffer = buffer if buffer is not None else TrajectoryStore(buffer_capacity, random_seed=random_seed)
@@ -61,8 +63,8 @@ def fit(model, env, test_env=None, n_steps=10, gamma=0.997, alpha=0.5, buffer=No
     key, test_key, sub = mz_random.split(key, 3)
     if model.params is None:
         model.init(sub, np.zeros((1, env.obs_dim), np.float32))
-    actor = VectorActor(model, env, buffer, n=n_steps, gamma=gamma, alpha=alpha, k_steps=k_steps,
-                        num_simulations=num_simulations)
+    actor = actor_cls(model, env, buffer, n=n_steps, gamma=gamma, alpha=alpha, k_steps=k_steps,
+                      num_simulations=num_simulations)
     steps_per_iteration = int(steps_per_iteration or max(1, getattr(env, "MAX_STEPS", 500) // 10))
     model_dir = model_save_path
     training_step, best_test_G, model_path, history = 0, -float("inf"), None, []

@@ -70,6 +70,12 @@ def test_fit_trains_on_the_gpu(tmp_path):
     after = model.params.prediction
     assert any(not np.array_equal(before[k], after[k]["w"]) for k in before)  # the learner's step reached the agent
     assert path is not None
+    # the same loop with the acting phase resident on the GPU (search kernel + CUDA graph per step)
+    from muax_b200.actor_device import CartPoleVecTorch, DeviceActor
+    _, hist_dev = fit(model, CartPoleVecTorch(256, seed=3), n_steps=10, k_steps=5, buffer_warm_up=32,
+                      steps_per_iteration=40, max_iterations=2, max_training_steps=10 ** 6, num_update_per_episode=5,
+                      num_trajectory=16, sample_per_trajectory=4, num_simulations=16, actor_cls=DeviceActor)
+    assert len(hist_dev) == 2 and all(np.isfinite(h["loss"]) for h in hist_dev) and hist_dev[-1]["episodes"] > 0
     other = muax_b200.MuZero(nn.create_muzero_network(nn.Representation, nn.Prediction, nn.Dynamic, 8, 2, 21), discount=0.997, support_size=10)
     other.init(muax_b200.random.PRNGKey(5), np.zeros((1, 4), np.float32))
     other.load(path)
