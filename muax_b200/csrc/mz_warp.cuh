@@ -4,17 +4,23 @@
 // lane2 (mz_lane2.cuh) runs 32 trees per CTA in lock step: nine CTA barriers per simulation, every phase as long as
 // the slowest tree's, 12 of 16 warps idle during the tree walks (profiles/r01_lane2_*: 33 % of the stall samples on
 // one barrier, 17k cycles per simulation).  A tree's simulations are a dependent chain, so the only way to finish an
-// act sooner is to shorten that chain.  Here a warp owns 4 trees (8 lanes each) for the whole act and never meets a
-// CTA barrier after the prologue:
-//   * dense layers: the two heads of a module form one 32-column matrix (re-laid out in shared memory once per
-//     CTA), a lane owns 4 adjacent columns -> one LDS.128 of weights per k (a quarter-warp reads one 128-byte row),
-//     activations are broadcast LDS.128 from the tree's scratch; 4 layers = 4 `__syncwarp`s;
+// act sooner is to shorten that chain.  Here a warp owns 32 / G trees (G = 16 lanes per tree by default, 8 as a
+// knob) for the whole act and never meets a CTA barrier after the prologue:
+//   * dense layers: the two heads of a module form one 32-column matrix (re-laid out in shared memory once per CTA
+//     from the TMA-staged blob), a lane owns U = 32 / G adjacent columns -> one LDS.64 / LDS.128 of weights per k (the
+//     lanes of a tree read one 128-byte row), activations are broadcast LDS.128 from the tree's scratch; 4 layers =
+//     4 `__syncwarp`s; ELU is evaluated branch-free on the U units at once;
 //   * categorical heads: reward head on the even lanes, value head on the odd lanes — exps and quotients dealt out
-//     4 ways, the two left-to-right float sums recomputed by every lane (same order as every other engine);
-//   * tree walks (select / expand / backup): lane2's scalar code on 16-byte records, executed redundantly by the 8
-//     lanes of a tree (identical values, identical stores), so no broadcast or vote is needed and the 4 trees of a
-//     warp only wait for each other's path length, not for 31 other trees;
-//   * tie-break noise rows (noise_table_kernel) are fetched one simulation ahead into registers (8 lanes x 16 B).
+//     G / 2 ways, the two left-to-right float sums recomputed by every lane (same order as every other engine);
+//   * selection is lane-parallel over the actions (lane x scores child x; min / max and the index-ordered argmax go
+//     through shuffles inside the tree's lanes); expand / backup are lane2's scalar code on 16-byte records, executed
+//     redundantly by the lanes of a tree (identical values, identical stores), so no broadcast or vote is needed and
+//     the trees of a warp only wait for each other's path length, not for 31 other trees;
+//   * tie-break noise: `producers` extra warps per CTA run the jax key chain of (tree, simulation) pairs ahead of the
+//     search into a ring of kWRing simulations guarded by full / empty mbarriers (lane = tree); with 0 producers the
+//     rows come from noise_table_kernel's table in HBM as in lane2;
+//   * every warp unpacks its own trees into the mctx SoA view when it finishes (no barrier before the dump); in the
+//     sharded multi-GPU act the outputs are also stored into the peers' gather buffers (LaneArgs::peer_delta).
 // Same arithmetic in the same order as lane2 / the CPU checkers: bit-identical (tests/test_gpu_parity.py).
 #pragma once
 #include "mz_lane2.cuh"
