@@ -209,7 +209,7 @@ class SearchEngine:
         weights = np.empty((B, A), np.float32)
         root_value = np.empty(B, np.float32)
         vp = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)  # noqa: E731
-        with torch.cuda.device(self.device):
+        with self._on_device():
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             rc = self.lib.mz_search_host(self._h, vp(obs), vp(inv), vp(nz), ctypes.byref(args), vp(action),
                                          vp(weights), vp(root_value), stream)
