@@ -17,7 +17,8 @@
 //     redundantly by the lanes of a tree (identical values, identical stores), so no broadcast or vote is needed and
 //     the trees of a warp only wait for each other's path length, not for 31 other trees;
 //   * tie-break noise: `producers` extra warps per CTA run the jax key chain of (tree, simulation) pairs ahead of the
-//     search into a ring of kWRing simulations guarded by full / empty mbarriers (lane = tree); with 0 producers the
+//     search into a ring of kWRing simulations guarded by full / empty mbarriers (lane = tree; every producer lane
+//     arrives on `full`, every search lane on `empty`); with 0 producers the
 //     rows come from noise_table_kernel's table in HBM as in lane2;
 //   * every warp unpacks its own trees into the mctx SoA view when it finishes (no barrier before the dump); in the
 //     sharded multi-GPU act the outputs are also stored into the peers' gather buffers (LaneArgs::peer_delta).
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
   if (tid == 0) {
     for (int i = 0; i < kWRing; ++i) {
       mbar_init(&nz_full[i], 32);          // every lane of the producing warp arrives
-      mbar_init(&nz_empty[i], (uint32_t)SW);  // lane 0 of every search warp arrives
+      mbar_init(&nz_empty[i], (uint32_t)(32 * SW));  // every lane of every search warp arrives (releases its own reads)
     }
     mbar_init(&wbar, 1);
     mbar_expect_tx(&wbar, (uint32_t)(round_up(net.packed_floats, 4) * 4));
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
       if (live && l == 0) a.out.sim_depth[(size_t)b * NS + sim] = depth;
     }
     __syncwarp();
-    if (in_kernel_noise && lane == 0) mbar_arrive(&nz_empty[sim % kWRing]);  // this warp is done with the ring slot
+    if (in_kernel_noise) mbar_arrive(&nz_empty[sim % kWRing]);  // this lane is done with the ring slot
     // recurrent_fn (muax/model.py:265-282): Dynamic -> min-max -> Prediction -> reward / value transforms
     float x[E];
     w_load<E>(temb + parent * E, x);
