@@ -194,9 +194,8 @@ def run_ours(args, wl, name):
                        dyn_minmax=wl["minmax"], discount=0.99, device=dev)
     eng.set_weights(blob)
     engine_id = {"auto": _lib.ENGINE_AUTO, "stepwise": _lib.ENGINE_STEPWISE, "fused": _lib.ENGINE_FUSED,
-                 "fused_cta": _lib.ENGINE_FUSED_CTA, "fused_group": _lib.ENGINE_FUSED_GROUP,
-                 "fused_lane": _lib.ENGINE_FUSED_LANE, "fused_lane2": _lib.ENGINE_FUSED_LANE2,
-                 "fused_warp": _lib.ENGINE_FUSED_WARP, "resident": _lib.ENGINE_RESIDENT}[args.engine]
+                 "fused_warp": _lib.ENGINE_FUSED_WARP, "treewarp": _lib.ENGINE_TREEWARP,
+                 "resident": _lib.ENGINE_RESIDENT}[args.engine]
     obs_all = np.random.default_rng(1).standard_normal((GB, wl["obs_dim"])).astype(np.float32)
     obs_host = np.ascontiguousarray(obs_all[rank * B:(rank + 1) * B])
     obs_dev = torch.from_numpy(obs_host).to(dev)
@@ -264,6 +263,7 @@ def run_ours(args, wl, name):
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     dev_total_ms, host_total_ms, kern_total_ms = (float(x) for x in tot.tolist())
+    eng.search(np.array([0, 1000], np.uint32), obs=obs_dev, want_tree=True, **kw)  # untimed: the tree view for D
     depth = float(eng.tree()["sim_depth"].float().mean().item())
     if rank == 0:
         sims = GB * NS * args.steps
@@ -318,7 +318,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "stepwise", "fused", "fused_cta", "fused_group", "fused_lane", "fused_lane2", "fused_warp", "resident"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "stepwise", "fused", "fused_warp", "treewarp", "resident"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -12,7 +12,9 @@
  *   - every `*_dev` pointer is device memory on `mz_config.device`, caller-owned, borrowed for the
  *     duration of the stream-ordered call; `stream` is a cudaStream_t passed as void* (NULL = default);
  *   - a handle is NOT thread-safe; use one handle per (device, stream);
- *   - every function returns 0 on success; on failure a message is available from mz_last_error();
+ *   - every function returns MZ_OK (0) on success; on failure it returns MZ_ERR_INVALID_ARGUMENT (the caller passed
+ *     something the reference would reject with a ValueError / chex assertion) or MZ_ERR_RUNTIME (CUDA failure,
+ *     unsupported configuration, call out of sequence) and a message is available from mz_last_error();
  *   - the library never falls back to a CPU path: without a usable CUDA device mz_create fails.
  */
 #ifndef MZSEARCH_H_
@@ -24,6 +26,10 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+#define MZ_OK 0
+#define MZ_ERR_RUNTIME 1
+#define MZ_ERR_INVALID_ARGUMENT 2
 
 #define MZ_MAX_LAYERS 8
 #define MZ_MAX_ACTIONS 32
@@ -41,14 +47,17 @@ extern "C" {
 #define MZ_ACT_RELU 1
 
 #define MZ_ENGINE_AUTO 0
-#define MZ_ENGINE_STEPWISE 1 /* select / recurrent / backup kernels per simulation, trees in HBM */
-#define MZ_ENGINE_FUSED 2    /* one search launch per act, trees resident in shared memory (best fused variant) */
-#define MZ_ENGINE_FUSED_CTA 3   /* the CTA-phased fused variant explicitly (lane groups per tree, generic widths) */
-#define MZ_ENGINE_FUSED_GROUP 4 /* the warp-autonomous variant explicitly (8 lanes per tree, packed weights) */
-#define MZ_ENGINE_FUSED_LANE 5  /* the lane == tree variant explicitly (scalar tree code, any A <= 32) */
-#define MZ_ENGINE_FUSED_LANE2 6 /* its compile-time specialisation for the stock MLP shapes (MuZero policy) */
-#define MZ_ENGINE_FUSED_WARP 8  /* warp-autonomous specialisation: a warp owns 4 trees, no CTA barrier in the loop */
-#define MZ_ENGINE_RESIDENT 7    /* one launch per act, a CTA owns T trees kept in HBM/L2 (any shapes, any root mode) */
+#define MZ_ENGINE_STEPWISE 1 /* select / recurrent / backup kernels per simulation, trees in HBM (also the callback mode) */
+#define MZ_ENGINE_FUSED 2    /* the best one-launch engine for the configuration: warp, else tree-warp, else resident */
+/* 3..6 were the CTA-phased / group / lane / lane2 shared-memory engines of round 1 (retired) */
+#define MZ_ENGINE_RESIDENT 7    /* one launch per act, a CTA owns T trees kept in HBM/L2 (any shapes, weights streamed) */
+#define MZ_ENGINE_FUSED_WARP 8  /* warp-autonomous, trees in shared memory, compile-time shapes of the stock MLP family */
+#define MZ_ENGINE_TREEWARP 9    /* warp-autonomous, trees as records in L1/L2, weights in shared memory, any shapes */
+
+#define MZ_PRECISION_FP32 0 /* parity mode: every engine, bit-identical to the CPU checkers */
+#define MZ_PRECISION_BF16 1 /* throughput mode: recurrent_fn on tcgen05 tensor cores, bf16 operands, fp32 accumulate */
+
+#define MZ_FLAG_WANT_TREE 1u /* keep / produce the mctx.Tree view of the search (mz_get_tree); muax never reads it */
 
 /* One hk.Sequential of hk.Linear layers with an activation between layers (none after the last):
  * muax/nn.py:63-65, 77-84, 97-104.  Offsets are in floats into the weight blob; W is [in][out]
@@ -103,6 +112,8 @@ typedef struct mz_search_args {
   float value_scale;      /* qtransform_completed_by_mix_value, default 0.1 */
   float maxvisit_init;    /* qtransform_completed_by_mix_value, default 50 */
   uint32_t key0, key1;    /* the jax PRNGKey words */
+  uint32_t flags;         /* MZ_FLAG_* */
+  int32_t precision;      /* MZ_PRECISION_* */
 } mz_search_args;
 
 /* Device views of the search tree after a search (mctx.Tree field names).
@@ -171,6 +182,8 @@ int mz_expand_backup(mz_handle* h, int32_t sim, const float* reward_dev, const f
                      const float* prior_logits_dev, const float* value_dev, const float* next_emb_dev, void* stream);
 int mz_finish(mz_handle* h, int32_t* action_out_dev, float* action_weights_out_dev, void* stream);
 
+/* The tree of the last search; fails unless that search ran with MZ_FLAG_WANT_TREE (muax never reads
+ * PolicyOutput.search_tree, so the default act does not pay for the mctx SoA view). */
 int mz_get_tree(mz_handle* h, mz_tree_view* view);
 
 /* Number of kernels this library launched on behalf of the handle since creation. */

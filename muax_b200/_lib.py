@@ -12,10 +12,13 @@ POLICY_MUZERO, POLICY_GUMBEL = 0, 1
 QT_PARENT_AND_SIBLINGS, QT_COMPLETED_BY_MIX_VALUE = 0, 1
 PRNG_LEGACY, PRNG_PARTITIONABLE = 0, 1
 ACT_ELU, ACT_RELU = 0, 1
-ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_FUSED, ENGINE_FUSED_CTA, ENGINE_FUSED_GROUP, ENGINE_FUSED_LANE = 0, 1, 2, 3, 4, 5
-ENGINE_FUSED_LANE2 = 6
+ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_FUSED = 0, 1, 2
 ENGINE_RESIDENT = 7
 ENGINE_FUSED_WARP = 8
+ENGINE_TREEWARP = 9
+PRECISION_FP32, PRECISION_BF16 = 0, 1
+FLAG_WANT_TREE = 1
+OK, ERR_RUNTIME, ERR_INVALID_ARGUMENT = 0, 1, 2
 
 EXPORTS = ("mz_last_error", "mz_default_args", "mz_create", "mz_destroy", "mz_set_weights", "mz_search",
            "mz_search_host", "mz_set_peer_outputs", "mz_begin", "mz_select", "mz_expand_backup", "mz_finish", "mz_get_tree",
@@ -40,7 +43,8 @@ class SearchArgs(ctypes.Structure):
         "policy", "qtransform", "num_simulations", "max_depth", "max_considered", "global_batch", "batch_offset",
         "engine")] + [(n, ctypes.c_float) for n in (
             "temperature", "dirichlet_fraction", "dirichlet_alpha", "pb_c_init", "pb_c_base", "gumbel_scale",
-            "value_scale", "maxvisit_init")] + [("key0", ctypes.c_uint32), ("key1", ctypes.c_uint32)])
+            "value_scale", "maxvisit_init")] + [("key0", ctypes.c_uint32), ("key1", ctypes.c_uint32),
+                                                ("flags", ctypes.c_uint32), ("precision", ctypes.c_int32)])
 
 
 class TreeView(ctypes.Structure):
@@ -90,8 +94,8 @@ def load(build_if_missing=True):
 
 
 def check(rc, what="libmzsearch call"):
-    if rc != 0:
+    """MZ_ERR_INVALID_ARGUMENT -> ValueError (what the reference raises for bad arguments), anything else non-zero ->
+    RuntimeError; the text comes from mz_last_error()."""
+    if rc != OK:
         msg = load().mz_last_error().decode("utf-8", "replace")
-        if "out of range" in msg or "must be" in msg or "mismatch" in msg or "exceeds" in msg or "unknown" in msg:
-            raise ValueError(f"{what}: {msg}")
-        raise RuntimeError(f"{what}: {msg}")
+        raise (ValueError if rc == ERR_INVALID_ARGUMENT else RuntimeError)(f"{what}: {msg}")

@@ -12,15 +12,22 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.environ.get("MZ_LIB_OUT") or os.path.join(PKG, "libmzsearch.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
-HEADERS = [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_fused.cuh", "mz_group.cuh", "mz_lane.cuh",
-                                            "mz_lane2.cuh", "mz_warp.cuh", "mz_resident.cuh")] + [
-    os.path.join(ROOT, "include", f) for f in ("mz_math.h", "mzsearch.h")]
+INC = [os.path.join(ROOT, "include", f) for f in ("mz_math.h", "mzsearch.h")]
+
+
+def _h(*names):
+    return [os.path.join(HERE, f) for f in names] + INC
+
+
 # translation unit -> the headers it includes (a TU is rebuilt when it or one of these is newer than its object)
 UNITS = {
-    "mzsearch.cu": HEADERS,
-    "mz_resident.cu": [os.path.join(HERE, f) for f in ("mz_device.cuh", "mz_resident.cuh")] + [
-        os.path.join(ROOT, "include", f) for f in ("mz_math.h", "mzsearch.h")],
+    "mzsearch.cu": _h("mz_device.cuh", "mz_warp.cuh", "mz_treewarp.cuh", "mz_resident.cuh", "mz_recurrent_tc.cuh"),
+    "mz_warp.cu": _h("mz_device.cuh", "mz_warp.cuh"),
+    "mz_treewarp.cu": _h("mz_device.cuh", "mz_records.cuh", "mz_resident.cuh", "mz_treewarp.cuh"),
+    "mz_resident.cu": _h("mz_device.cuh", "mz_records.cuh", "mz_resident.cuh"),
+    "mz_recurrent_tc.cu": _h("mz_device.cuh", "mz_recurrent_tc.cuh"),
 }
+HEADERS = sorted({p for deps in UNITS.values() for p in deps})
 SOURCES = [os.path.join(HERE, u) for u in UNITS]
 DEPS = SOURCES + HEADERS
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -62,14 +69,23 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     os.makedirs(OBJ_DIR, exist_ok=True)
-    with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
-        results = list(pool.map(lambda u: _compile(u, force, verbose), UNITS))
-    objs = [o for o, _ in results]
-    res = subprocess.run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart=static",
-                          "-Xcompiler", "-fPIC", "-o", OUT] + objs, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed linking libmzsearch.so")
+    # several processes (torchrun ranks, xdist workers) may get here at once: one builds, the others wait for the
+    # lock and then find the library up to date; the link goes to a temporary name and is renamed into place
+    import fcntl
+    with open(os.path.join(OBJ_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and up_to_date():
+            return OUT
+        with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
+            results = list(pool.map(lambda u: _compile(u, force, verbose), UNITS))
+        objs = [o for o, _ in results]
+        tmp = f"{OUT}.{os.getpid()}.tmp"
+        res = subprocess.run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart=static",
+                              "-Xcompiler", "-fPIC", "-o", tmp] + objs, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed linking libmzsearch.so")
+        os.replace(tmp, OUT)
     if verbose:
         print("".join(log for _, log in results))
     return OUT

@@ -1,0 +1,32 @@
+// mz_recurrent_tc.cuh — interface of the tcgen05 recurrent_fn kernel (implementation: mz_recurrent_tc.cu).
+//
+// Throughput mode of the search (mz_search_args.precision = MZ_PRECISION_BF16): muax's `_recurrent_inference`
+// (muax/model.py:265-282: Dynamic MLP -> min-max -> Prediction MLP -> 2x support_to_scalar(softmax)) for the whole
+// batch of trees awaiting expansion as ONE kernel whose dense layers run on the 5th-generation tensor cores:
+// 128-row tiles, bf16 operands (activations rounded per layer, weights pre-packed once per mz_set_weights), fp32
+// accumulation in tensor memory, weights staged into shared memory by TMA bulk copies.
+#pragma once
+#include <string>
+
+#include "mz_device.cuh"
+
+namespace mz {
+
+struct RecurrentTcState {
+  bool available = false;   // the network shapes fit the kernel (see recurrent_tc_init)
+  std::string why;          // ... and if not, why
+  void* impl = nullptr;
+};
+
+int recurrent_tc_init(RecurrentTcState& st, const Net& net, int batch, int device, std::string* err);
+void recurrent_tc_destroy(RecurrentTcState& st);
+// Re-packs the raw fp32 blob (device) into the bf16 UMMA operand images; call after every mz_set_weights.
+int recurrent_tc_pack(RecurrentTcState& st, const Net& net, const float* raw_weights_dev, cudaStream_t stream,
+                      int64_t* launches);
+// recurrent_fn for all B rows: embeddings[b, parent[b]] and action[b] -> reward[b], value[b], prior logits [b, A],
+// next embedding [b, E] (the I/O of the fp32 recurrent_kernel of mzsearch.cu).
+int recurrent_tc_launch(RecurrentTcState& st, const Net& net, const Tree& t, const int32_t* parent,
+                        const int32_t* action, float* reward, float* value, float* logits, float* next_emb,
+                        cudaStream_t stream, int64_t* launches, std::string* err);
+
+}  // namespace mz

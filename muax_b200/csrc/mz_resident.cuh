@@ -50,6 +50,12 @@ int resident_launch(ResidentState& st, const Net& net, const float* weights, con
                     const uint8_t* invalid, const float* noise, int32_t* action_out, float* weights_out,
                     float* root_value_out, cudaStream_t stream, int64_t* launches, std::string* err);
 
+// Shared with the tree-warp engine (mz_treewarp.cu), which keeps its trees in the same record arrays:
+int net_weight_bytes(const Net& net);  // bytes of the raw fp32 blob the stacks address, rounded up to 16
+int records_reserve(ResidentState& st, int B, int NS, int A, int PL, std::string* err);
+int records_noise_prepass(ResidentState& st, const SearchParams& p, int B, int A, int levels, int PL,
+                          cudaStream_t stream, int64_t* launches, int* K_out, std::string* err);
+
 // Records of the last search -> the handle's SoA arrays (no-op unless a resident search ran since the last call).
 int resident_unpack(ResidentState& st, const Tree& tree, float gamma, std::string* err);
 

@@ -6,7 +6,9 @@
 //   expand_backup (mctx expand scatter + backward, Appendix A.3)          warp lane-group per tree
 // bracketed by root (muax/model.py:251-263), begin (policy prologue A.2/A.4 + instantiate_tree_from_root)
 // and finish (summary + temperature + categorical, or the Gumbel epilogue).
-// The fused persistent engine lives in mz_fused.cuh.
+// The one-launch engines live in their own translation units: mz_warp.cu (headline shapes, trees in shared memory),
+// mz_treewarp.cu (any net whose weights fit shared memory, trees as records in L1/L2), mz_resident.cu (wide nets,
+// weights streamed), mz_recurrent_tc.cu (tcgen05 recurrent_fn of the bf16 throughput mode).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -15,13 +17,13 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "mz_device.cuh"
-#include "mz_fused.cuh"
-#include "mz_group.cuh"
-#include "mz_lane.cuh"
-#include "mz_lane2.cuh"
-#include "mz_warp.cuh"
+#include "mz_recurrent_tc.cuh"
 #include "mz_resident.cuh"
+#include "mz_treewarp.cuh"
+#include "mz_warp.cuh"
 
 namespace mz {
 
@@ -29,9 +31,13 @@ namespace mz {
 
 static thread_local std::string g_last_error;
 
-static int fail(const std::string& msg) {
+static int fail(const std::string& msg) {  // runtime failure (CUDA error, unsupported configuration, misuse of state)
   g_last_error = msg;
-  return 1;
+  return MZ_ERR_RUNTIME;
+}
+static int fail_arg(const std::string& msg) {  // the caller passed an invalid argument (Python: ValueError)
+  g_last_error = msg;
+  return MZ_ERR_INVALID_ARGUMENT;
 }
 
 #define MZ_CUDA(expr)                                                                                   \
@@ -329,11 +335,13 @@ struct mz_handle {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   bool timed = false;
   std::vector<void*> allocs;
-  mz::FusedState fused;
-  mz::GroupState group;
-  mz::LaneState lanes;
-  mz::Lane2State lane2;
   mz::WarpState warpeng;
+  mz::TreeWarpState treewarp;
+  mz::RecurrentTcState rtc;
+  mz::SimKeys host_keys{};      // simulate keys of the call in flight (host copy)
+  bool keys_on_device = false;  // ... and whether they have been staged into sim_keys_dev
+  int key_slot = 0;
+  bool tree_valid = false;      // the SoA tree view describes the last search (want_tree, or an engine that always has it)
   std::vector<int64_t> peer_deltas;  // mz_set_peer_outputs
   mz::ResidentState resident;
 };
@@ -358,13 +366,13 @@ static int stack_max_width(const mz_stack& s, int cur) {
 }
 
 static int validate_stack(const mz_stack& s, int in, int out, const char* name, size_t* need) {
-  if (s.n_layers < 1 || s.n_layers > MZ_MAX_LAYERS) return fail(std::string(name) + ": n_layers out of range");
-  if (s.in_dim[0] != in) return fail(std::string(name) + ": first layer input width mismatch");
-  if (s.out_dim[s.n_layers - 1] != out) return fail(std::string(name) + ": last layer output width mismatch");
+  if (s.n_layers < 1 || s.n_layers > MZ_MAX_LAYERS) return fail_arg(std::string(name) + ": n_layers out of range");
+  if (s.in_dim[0] != in) return fail_arg(std::string(name) + ": first layer input width mismatch");
+  if (s.out_dim[s.n_layers - 1] != out) return fail_arg(std::string(name) + ": last layer output width mismatch");
   for (int l = 0; l < s.n_layers; ++l) {
-    if (s.in_dim[l] < 1 || s.out_dim[l] < 1) return fail(std::string(name) + ": bad layer width");
-    if (l > 0 && s.in_dim[l] != s.out_dim[l - 1]) return fail(std::string(name) + ": layer widths do not chain");
-    if (s.w_off[l] < 0 || s.b_off[l] < 0) return fail(std::string(name) + ": negative offset");
+    if (s.in_dim[l] < 1 || s.out_dim[l] < 1) return fail_arg(std::string(name) + ": bad layer width");
+    if (l > 0 && s.in_dim[l] != s.out_dim[l - 1]) return fail_arg(std::string(name) + ": layer widths do not chain");
+    if (s.w_off[l] < 0 || s.b_off[l] < 0) return fail_arg(std::string(name) + ": negative offset");
     *need = std::max(*need, (size_t)s.w_off[l] + (size_t)s.in_dim[l] * s.out_dim[l]);
     *need = std::max(*need, (size_t)s.b_off[l] + (size_t)s.out_dim[l]);
   }
@@ -388,20 +396,23 @@ static int tree_blocks(const mz_handle* h) { return (h->cfg.batch * h->G + kTree
   } while (0)
 
 static int check_args(const mz_handle* h, const mz_search_args* a) {
-  if (a == nullptr) return fail("args is NULL");
-  if (a->policy != MZ_POLICY_MUZERO && a->policy != MZ_POLICY_GUMBEL) return fail("unknown policy");
-  if (a->qtransform != 0 && a->qtransform != 1) return fail("unknown qtransform");
+  if (a == nullptr) return fail_arg("args is NULL");
+  if (a->policy != MZ_POLICY_MUZERO && a->policy != MZ_POLICY_GUMBEL) return fail_arg("unknown policy");
+  if (a->qtransform != 0 && a->qtransform != 1) return fail_arg("unknown qtransform");
+  if (a->precision != MZ_PRECISION_FP32 && a->precision != MZ_PRECISION_BF16) return fail_arg("unknown precision");
   if (a->num_simulations < 0 || a->num_simulations > h->cfg.max_num_simulations)
-    return fail("num_simulations exceeds the handle's max_num_simulations");
+    return fail_arg("num_simulations exceeds the handle's max_num_simulations");
   if (a->policy == MZ_POLICY_GUMBEL && (a->max_considered < 0 || a->max_considered > 1024))
-    return fail("max_num_considered_actions out of range");
+    return fail_arg("max_num_considered_actions out of range");
   const int gbatch = a->global_batch > 0 ? a->global_batch : h->cfg.batch;
   if (a->batch_offset < 0 || a->batch_offset + h->cfg.batch > gbatch)
-    return fail("batch_offset + batch exceeds global_batch");
+    return fail_arg("batch_offset + batch exceeds global_batch");
   return 0;
 }
 
-// Derive all keys of one act on the host (scalar chain, identical for every tree) and stage them.
+// Derive all keys of one act on the host (scalar chain, identical for every tree).  The per-simulation simulate keys
+// stay on the host (h->host_keys) until an engine needs them: engines that take them in their kernel parameters
+// (SimKeys, searches of at most kInlineSims simulations) never pay an H2D copy; the others call ensure_device_keys.
 static int stage_keys(mz_handle* h, const mz_search_args* a, cudaStream_t stream) {
   SearchParams& p = h->params;
   const int mode = h->cfg.prng_mode;
@@ -440,8 +451,13 @@ static int stage_keys(mz_handle* h, const mz_search_args* a, cudaStream_t stream
   // simulate keys: rng_key, simulate_key, expand_key = split(rng_key, 3) per simulation
   const int slot = h->next_slot;
   h->next_slot = (slot + 1) % mz_handle::kSlots;
-  MZ_CUDA(cudaEventSynchronize(h->slot_done[slot]));
-  uint32_t* keys = h->key_slots + (size_t)slot * 2 * (h->cfg.max_num_simulations + 1);
+  h->key_slot = slot;
+  const bool inline_ok = NS <= kInlineSims;
+  uint32_t* keys = h->host_keys.w;
+  if (!inline_ok) {  // long searches stage through the pinned ring: the slot must have been consumed by its last copy
+    MZ_CUDA(cudaEventSynchronize(h->slot_done[slot]));
+    keys = h->key_slots + (size_t)slot * 2 * (h->cfg.max_num_simulations + 1);
+  }
   uint32_t cur[2] = {search_key[0], search_key[1]};
   for (int s = 0; s < NS; ++s) {
     uint32_t nxt[2];
@@ -450,10 +466,8 @@ static int stage_keys(mz_handle* h, const mz_search_args* a, cudaStream_t stream
     cur[0] = nxt[0];
     cur[1] = nxt[1];
   }
-  if (NS > 0)
-    MZ_CUDA(cudaMemcpyAsync(h->sim_keys_dev, keys, sizeof(uint32_t) * 2 * NS, cudaMemcpyHostToDevice, stream));
-  MZ_CUDA(cudaEventRecord(h->slot_done[slot], stream));
-  p.sim_keys = h->sim_keys_dev;
+  h->keys_on_device = false;
+  p.sim_keys = nullptr;
   p.considered_table = nullptr;
   if (a->policy == MZ_POLICY_GUMBEL) {
     const int M = a->max_considered;
@@ -474,6 +488,24 @@ static int stage_keys(mz_handle* h, const mz_search_args* a, cudaStream_t stream
     }
     p.considered_table = h->table_dev;
   }
+  return 0;
+}
+
+// The simulate keys of the call in flight -> device memory (h->params.sim_keys), once per call.
+static int ensure_device_keys(mz_handle* h, cudaStream_t stream) {
+  if (h->keys_on_device) return 0;
+  const int NS = h->params.num_simulations;
+  const int slot = h->key_slot;
+  uint32_t* pinned = h->key_slots + (size_t)slot * 2 * (h->cfg.max_num_simulations + 1);
+  if (NS <= kInlineSims) {  // the keys were derived into host_keys: move them into this call's pinned slot
+    MZ_CUDA(cudaEventSynchronize(h->slot_done[slot]));
+    std::memcpy(pinned, h->host_keys.w, sizeof(uint32_t) * 2 * NS);
+  }
+  if (NS > 0)
+    MZ_CUDA(cudaMemcpyAsync(h->sim_keys_dev, pinned, sizeof(uint32_t) * 2 * NS, cudaMemcpyHostToDevice, stream));
+  MZ_CUDA(cudaEventRecord(h->slot_done[slot], stream));
+  h->params.sim_keys = h->sim_keys_dev;
+  h->keys_on_device = true;
   return 0;
 }
 
@@ -501,6 +533,7 @@ static int clear_tree(mz_handle* h, int NS, bool clear_embeddings, cudaStream_t 
 static int launch_begin(mz_handle* h, const float* root_logits, const float* root_value, const float* root_emb,
                         const uint8_t* invalid, const float* noise, cudaStream_t stream) {
   h->has_invalid = invalid != nullptr;
+  if (ensure_device_keys(h, stream)) return 1;  // select_kernel derives the per-tree keys from them
   if (clear_tree(h, h->params.num_simulations, h->params.max_depth > 0, stream)) return 1;
   MZ_DISPATCH_G(h, begin_kernel, tree_blocks(h), stream, h->tree, h->params, root_logits, root_value, root_emb,
                 invalid, noise);
@@ -520,8 +553,29 @@ static int launch_root(mz_handle* h, const float* obs, const float* emb_in, cuda
   return 0;
 }
 
-static int run_stepwise(mz_handle* h, cudaStream_t stream) {
+// Throughput mode: the stepwise tree kernels around the tcgen05 recurrent kernel.
+static int run_stepwise_tc(mz_handle* h, cudaStream_t stream) {
+  if (!h->rtc.available)
+    return fail("precision = bf16: the tcgen05 recurrent kernel does not cover this network (" + h->rtc.why + ")");
+  const int NS = h->params.num_simulations;
+  std::string err;
+  for (int sim = 0; sim < NS; ++sim) {
+    SelectIO sio{h->sel_parent, h->sel_action, h->sel_next, nullptr, nullptr};
+    MZ_DISPATCH_G(h, select_kernel, tree_blocks(h), stream, h->tree, h->params, sim, sio);
+    if (recurrent_tc_launch(h->rtc, h->net, h->tree, h->sel_parent, h->sel_action, h->rec_reward, h->rec_value,
+                            h->rec_logits, h->rec_emb, stream, &h->launches, &err))
+      return fail(err);
+    ExpandIO eio{h->sel_parent, h->sel_action, h->sel_next, h->rec_reward, nullptr, h->rec_value, h->rec_logits,
+                 h->rec_emb};
+    MZ_DISPATCH_G(h, expand_backup_kernel, tree_blocks(h), stream, h->tree, h->params, eio);
+  }
+  MZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int run_stepwise(mz_handle* h, cudaStream_t stream, int precision) {
   if (h->weights == nullptr) return fail("mz_set_weights has not been called");
+  if (precision == MZ_PRECISION_BF16) return run_stepwise_tc(h, stream);
   const int NS = h->params.num_simulations;
   const int grid_mlp = (h->cfg.batch + kMlpRows - 1) / kMlpRows;
   for (int sim = 0; sim < NS; ++sim) {
@@ -547,82 +601,70 @@ static int launch_finish(mz_handle* h, int32_t* action_out, float* weights_out, 
 static int search_device(mz_handle* h, const float* obs, const float* root_logits, const float* root_value,
                          const float* root_emb, const uint8_t* invalid, const float* noise, const mz_search_args* args,
                          int32_t* action_out, float* weights_out, float* root_value_out, cudaStream_t stream) {
-  if (check_args(h, args)) return 1;
-  if (action_out == nullptr || weights_out == nullptr) return fail("action / action_weights outputs are required");
-  if (obs == nullptr && root_emb == nullptr) return fail("give obs, or root_emb (optionally with root_logits + root_value)");
+  if (int rc = check_args(h, args)) return rc;
+  if (action_out == nullptr || weights_out == nullptr) return fail_arg("action / action_weights outputs are required");
+  if (obs == nullptr && root_emb == nullptr)
+    return fail_arg("give obs, or root_emb (optionally with root_logits + root_value)");
   if (obs == nullptr && ((root_logits == nullptr) != (root_value == nullptr)))
-    return fail("root_logits and root_value must be given together");
+    return fail_arg("root_logits and root_value must be given together");
+  if (obs != nullptr && h->cfg.obs_dim <= 0)
+    return fail_arg("handle was created with obs_dim = 0: supply the root embedding instead of obs");
   MZ_CUDA(cudaSetDevice(h->cfg.device));
-  if (stage_keys(h, args, stream)) return 1;
+  if (int rc = stage_keys(h, args, stream)) return rc;
   h->resident.dirty = false;  // whatever runs next owns the SoA tree view
+  h->tree_valid = false;
+  const bool want_tree = (args->flags & MZ_FLAG_WANT_TREE) != 0;
   MZ_CUDA(cudaEventRecord(h->ev_start, stream));
   int engine = args->engine;
-  const bool have_w = obs != nullptr && h->weights != nullptr;
-  const bool lane_ok = have_w && lane_supported(h->lanes, h->params);
-  const bool group_ok = have_w && group_supported(h->group, h->params, h->cfg.batch);
-  const bool fused_ok = have_w && fused_supported(h->fused, h->net, h->params);
-  const bool lane2_ok = lane_ok && lane2_supported(h->lane2, h->lanes, h->params);
-  const bool warp_ok = have_w && h->lanes.available && warp_supported(h->warpeng, h->lanes, h->params, h->cfg.batch);
-  const bool resident_ok = h->weights != nullptr && resident_supported(h->resident, h->net, h->cfg.batch, h->params.num_simulations);
-  enum { kLane = 100, kLane2 = 101, kWarp = 102 };
-  // AUTO: the shared-memory engines when the trees fit on chip (measured on B200, profiles/: warp engine first, then
-  // lane2 0.43 ms, group 0.72 ms per act at the headline shapes), else the CTA-resident engine (trees in HBM/L2, one launch per act);
-  // the stepwise engine remains for the callback mode and as the reference implementation of the kernels.
-  if (engine == MZ_ENGINE_AUTO)
-    engine = (warp_ok || lane2_ok || group_ok) ? MZ_ENGINE_FUSED
-                                    : (resident_ok ? MZ_ENGINE_RESIDENT
-                                                   : ((lane_ok || fused_ok) ? MZ_ENGINE_FUSED : MZ_ENGINE_STEPWISE));
-  if (engine == MZ_ENGINE_FUSED)
-    engine = warp_ok ? (int)kWarp : lane2_ok ? (int)kLane2 : (group_ok ? MZ_ENGINE_FUSED_GROUP : (lane_ok ? (int)kLane : MZ_ENGINE_FUSED_CTA));
-  if (engine == MZ_ENGINE_FUSED_LANE) engine = kLane;
-  if (engine == MZ_ENGINE_FUSED_LANE2) engine = kLane2;
-  if (engine == MZ_ENGINE_FUSED_WARP) engine = kWarp;
-  if (!h->peer_deltas.empty() && engine != kWarp)
+  const bool have_w = h->weights != nullptr;
+  const int B = h->cfg.batch, NS = h->params.num_simulations;
+  const bool warp_ok = have_w && obs != nullptr && warp_supported(h->warpeng, h->params, B);
+  const bool treewarp_ok = have_w && treewarp_supported(h->treewarp, h->net, B, NS, h->params.max_depth);
+  const bool resident_ok = have_w && resident_supported(h->resident, h->net, B, NS);
+  if (args->precision == MZ_PRECISION_BF16) {
+    // throughput mode: the stepwise kernels around the tcgen05 recurrent kernel (mz_recurrent_tc.cu)
+    if (engine != MZ_ENGINE_AUTO && engine != MZ_ENGINE_STEPWISE)
+      return fail_arg("precision = bf16 runs on the stepwise engine (engine must be AUTO or STEPWISE)");
+    engine = MZ_ENGINE_STEPWISE;
+  }
+  // AUTO: the warp engine when its compile-time shapes match and the trees fit on chip; else the tree-warp engine
+  // (weights in shared memory, trees as records in L1/L2); else the CTA-resident engine (weights streamed); the
+  // stepwise engine remains for the callback mode, the bf16 throughput mode and as the reference implementation.
+  if (engine == MZ_ENGINE_AUTO || engine == MZ_ENGINE_FUSED)
+    engine = warp_ok ? MZ_ENGINE_FUSED_WARP
+                     : (treewarp_ok ? MZ_ENGINE_TREEWARP : (resident_ok ? MZ_ENGINE_RESIDENT : MZ_ENGINE_STEPWISE));
+  if (!h->peer_deltas.empty() && engine != MZ_ENGINE_FUSED_WARP)
     return fail("peer outputs (mz_set_peer_outputs) are written by the warp engine only; this configuration runs on "
                 "another engine — clear them and exchange the outputs with a collective");
-  if (engine == MZ_ENGINE_RESIDENT) {
-    if (!resident_ok) return fail("the resident engine does not support this configuration (see DESIGN.md)");
-    if (obs != nullptr && h->cfg.obs_dim <= 0)
-      return fail("handle was created with obs_dim = 0: supply the root embedding instead of obs");
-    h->has_invalid = invalid != nullptr;
-    std::string err;
-    if (resident_launch(h->resident, h->net, h->weights, h->tree, h->params, obs, root_emb, root_logits, root_value,
-                        invalid, noise, action_out, weights_out, root_value_out, stream, &h->launches, &err))
+  h->has_invalid = invalid != nullptr;
+  std::string err;
+  if (engine == MZ_ENGINE_RESIDENT || engine == MZ_ENGINE_TREEWARP) {
+    if (engine == MZ_ENGINE_RESIDENT ? !resident_ok : !treewarp_ok)
+      return fail("this one-launch engine does not support this configuration (see DESIGN.md)");
+    if (ensure_device_keys(h, stream)) return 1;
+    const int rc =
+        engine == MZ_ENGINE_RESIDENT
+            ? resident_launch(h->resident, h->net, h->weights, h->tree, h->params, obs, root_emb, root_logits,
+                              root_value, invalid, noise, action_out, weights_out, root_value_out, stream, &h->launches,
+                              &err)
+            : treewarp_launch(h->treewarp, h->resident, h->net, h->weights, h->tree, h->params, obs, root_emb,
+                              root_logits, root_value, invalid, noise, action_out, weights_out, root_value_out, stream,
+                              &h->launches, &err);
+    if (rc) return fail(err);
+    h->tree_valid = true;  // the records are unpacked lazily by mz_get_tree
+  } else if (engine == MZ_ENGINE_FUSED_WARP) {
+    if (!warp_ok)
+      return fail(std::string("this one-launch engine does not support this configuration (see DESIGN.md)") +
+                  (!h->warpeng.available ? " [warp engine: no compiled shape variant]"
+                                         : " [warp engine: policy / qtransform / root mode / size]"));
+    if (want_tree && args->num_simulations + 1 < h->N && clear_tree(h, args->num_simulations, true, stream)) return 1;
+    const bool inline_keys = NS <= kInlineSims && h->warpeng.producers > 0;
+    if (!inline_keys && ensure_device_keys(h, stream)) return 1;
+    if (warp_launch(h->warpeng, h->tree, h->params, inline_keys ? &h->host_keys : nullptr, obs, invalid, noise,
+                    action_out, weights_out, root_value_out, h->peer_deltas, want_tree, stream, &h->launches, &err))
       return fail(err);
-  } else if (engine == kLane || engine == kLane2 || engine == kWarp || engine == MZ_ENGINE_FUSED_CTA || engine == MZ_ENGINE_FUSED_GROUP) {
-    if ((engine == MZ_ENGINE_FUSED_CTA && !fused_ok) || (engine == MZ_ENGINE_FUSED_GROUP && !group_ok) ||
-        (engine == kLane && !lane_ok) || (engine == kLane2 && !lane2_ok) || (engine == kWarp && !warp_ok))
-      return fail(std::string("the fused engine does not support this configuration (see DESIGN.md)") +
-                  (engine == kWarp ? (h->warpeng.variant == nullptr ? " [warp engine: no compiled shape variant]"
-                                                                    : (h->lanes.available ? " [warp engine: policy / qtransform / size]"
-                                                                                        : " [warp engine: lane packing unavailable]"))
-                                   : ""));
-    h->has_invalid = invalid != nullptr;
-    if (args->num_simulations + 1 < h->N && clear_tree(h, args->num_simulations, true, stream)) return 1;
-    std::string err;
-    if (engine == kWarp) {
-      if (warp_launch(h->warpeng, h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
-                      root_value_out, h->peer_deltas, stream, &h->launches, &err))
-        return fail(err);
-    } else if (engine == kLane2) {
-      if (lane2_launch(h->lane2, h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
-                       root_value_out, stream, &h->launches, &err))
-        return fail(err);
-    } else if (engine == kLane) {
-      if (lane_launch(h->lanes, h->tree, h->params, obs, invalid, noise, action_out, weights_out, root_value_out,
-                      stream, &h->launches, &err))
-        return fail(err);
-    } else if (engine == MZ_ENGINE_FUSED_GROUP) {
-      if (group_launch(h->group, h->tree, h->params, obs, invalid, noise, action_out, weights_out, root_value_out,
-                       stream, &h->launches, &err))
-        return fail(err);
-    } else {
-      if (fused_launch(h->fused, h->net, h->weights, h->tree, h->params, obs, invalid, noise, action_out, weights_out,
-                       root_value_out, stream, &err))
-        return fail(err);
-      h->launches += 1;
-    }
-  } else {
+    h->tree_valid = want_tree;
+  } else if (engine == MZ_ENGINE_STEPWISE) {
     if (obs != nullptr || root_logits == nullptr) {  // Prediction (and Representation) run in the library
       if (launch_root(h, obs, obs != nullptr ? nullptr : root_emb, stream)) return 1;
       root_logits = h->root_logits;
@@ -633,8 +675,11 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
       MZ_CUDA(cudaMemcpyAsync(root_value_out, root_value, sizeof(float) * h->cfg.batch, cudaMemcpyDefault,
                               stream));
     if (launch_begin(h, root_logits, root_value, root_emb, invalid, noise, stream)) return 1;
-    if (run_stepwise(h, stream)) return 1;
+    if (run_stepwise(h, stream, args->precision)) return 1;
     if (launch_finish(h, action_out, weights_out, stream)) return 1;
+    h->tree_valid = true;
+  } else {
+    return fail_arg("unknown engine");
   }
   MZ_CUDA(cudaEventRecord(h->ev_stop, stream));
   h->timed = true;
@@ -666,28 +711,31 @@ void mz_default_args(mz_search_args* a) {
   a->value_scale = 0.1f;
   a->maxvisit_init = 50.0f;
   a->engine = MZ_ENGINE_AUTO;
+  a->flags = 0;  // no tree view unless asked for (MZ_FLAG_WANT_TREE): muax never reads PolicyOutput.search_tree
+  a->precision = MZ_PRECISION_FP32;
 }
 
 int mz_create(mz_handle** out, const mz_config* cfg) {
   using namespace mz;
-  if (out == nullptr || cfg == nullptr) return fail("mz_create: NULL argument");
+  if (out == nullptr || cfg == nullptr) return fail_arg("mz_create: NULL argument");
   *out = nullptr;
-  if (cfg->batch < 1) return fail("batch must be >= 1");
-  if (cfg->num_actions < 1 || cfg->num_actions > MZ_MAX_ACTIONS) return fail("num_actions must be in 1..32");
-  if (cfg->embed_dim < 1) return fail("embed_dim must be >= 1");
-  if (cfg->support_size < 0) return fail("support_size must be >= 0");
-  if (cfg->max_num_simulations < 0) return fail("max_num_simulations must be >= 0");
+  if (cfg->batch < 1) return fail_arg("batch must be >= 1");
+  if (cfg->num_actions < 1 || cfg->num_actions > MZ_MAX_ACTIONS) return fail_arg("num_actions must be in 1..32");
+  if (cfg->embed_dim < 1) return fail_arg("embed_dim must be >= 1");
+  if (cfg->support_size < 0) return fail_arg("support_size must be >= 0");
+  if (cfg->max_num_simulations < 0) return fail_arg("max_num_simulations must be >= 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("no CUDA device: libmzsearch has no CPU fallback");
-  if (cfg->device < 0 || cfg->device >= ndev) return fail("device ordinal out of range");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail_arg("device ordinal out of range");
   const int F = 2 * cfg->support_size + 1;
   size_t need = 0;
-  if (cfg->obs_dim > 0 && validate_stack(cfg->repr, cfg->obs_dim, cfg->embed_dim, "repr", &need)) return 1;
-  if (validate_stack(cfg->pred_v, cfg->embed_dim, F, "pred_v", &need)) return 1;
-  if (validate_stack(cfg->pred_pi, cfg->embed_dim, cfg->num_actions, "pred_pi", &need)) return 1;
-  if (validate_stack(cfg->dyn_ns, cfg->embed_dim + cfg->num_actions, cfg->embed_dim, "dyn_ns", &need)) return 1;
-  if (validate_stack(cfg->dyn_r, cfg->embed_dim + cfg->num_actions, F, "dyn_r", &need)) return 1;
+  if (cfg->obs_dim > 0)
+    if (int rc = validate_stack(cfg->repr, cfg->obs_dim, cfg->embed_dim, "repr", &need)) return rc;
+  if (int rc = validate_stack(cfg->pred_v, cfg->embed_dim, F, "pred_v", &need)) return rc;
+  if (int rc = validate_stack(cfg->pred_pi, cfg->embed_dim, cfg->num_actions, "pred_pi", &need)) return rc;
+  if (int rc = validate_stack(cfg->dyn_ns, cfg->embed_dim + cfg->num_actions, cfg->embed_dim, "dyn_ns", &need)) return rc;
+  if (int rc = validate_stack(cfg->dyn_r, cfg->embed_dim + cfg->num_actions, F, "dyn_r", &need)) return rc;
   MZ_CUDA(cudaSetDevice(cfg->device));
   mz_handle* h = new mz_handle();
   h->cfg = *cfg;
@@ -719,7 +767,7 @@ int mz_create(mz_handle** out, const mz_config* cfg) {
   const size_t smem = mlp_smem_bytes(net);
   if (smem > 200 * 1024) {
     delete h;
-    return fail("layer width too large for the MLP kernels' shared-memory staging");
+    return fail_arg("layer width too large for the MLP kernels' shared-memory staging");
   }
   auto bail = [&](int rc) {
     if (rc) mz_destroy(h);
@@ -793,14 +841,12 @@ int mz_create(mz_handle** out, const mz_config* cfg) {
   MZ_TRY(cudaEventCreate(&h->ev_stop) != cudaSuccess ? fail("cudaEventCreate failed") : 0);
   {
     std::string err;
-    if (fused_init(h->fused, h->net, cfg->batch, cfg->max_num_simulations, cfg->device, &err) ||
-        group_init(h->group, h->net, cfg->device, &err) || lane_init(h->lanes, h->net, cfg->device, &err) ||
-        resident_init(h->resident, h->net, cfg->device, &err)) {
+    if (warp_init(h->warpeng, h->net, cfg->device, &err) || treewarp_init(h->treewarp, h->net, cfg->device, &err) ||
+        resident_init(h->resident, h->net, cfg->device, &err) ||
+        recurrent_tc_init(h->rtc, h->net, cfg->batch, cfg->device, &err)) {
       mz_destroy(h);
       return fail(err);
     }
-    lane2_init(h->lane2, h->lanes, h->net, h->lanes.max_smem);
-    warp_init(h->warpeng, h->lanes, h->net, h->lanes.max_smem);
   }
 #undef MZ_TRY
   *out = h;
@@ -811,10 +857,9 @@ int mz_destroy(mz_handle* h) {
   if (h == nullptr) return 0;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
-  mz::fused_destroy(h->fused);
-  mz::group_destroy(h->group);
-  mz::lane_destroy(h->lanes);
+  mz::warp_destroy(h->warpeng);
   mz::resident_destroy(h->resident);
+  mz::recurrent_tc_destroy(h->rtc);
   for (void* p : h->allocs) cudaFree(p);
   if (h->weights) cudaFree(h->weights);
   if (h->table_dev) cudaFree(h->table_dev);
@@ -832,15 +877,16 @@ int mz_destroy(mz_handle* h) {
 
 int mz_set_weights(mz_handle* h, const float* blob, size_t n_floats, int on_device, void* stream) {
   using namespace mz;
-  if (h == nullptr || blob == nullptr) return fail("mz_set_weights: NULL argument");
-  if (n_floats < h->n_weights) return fail("weight blob is smaller than the layer offsets require");
+  if (h == nullptr || blob == nullptr) return fail_arg("mz_set_weights: NULL argument");
+  if (n_floats < h->n_weights) return fail_arg("weight blob is smaller than the layer offsets require");
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   if (h->weights == nullptr) MZ_CUDA(cudaMalloc((void**)&h->weights, std::max(h->n_weights, (size_t)4) * sizeof(float) + 16));
   MZ_CUDA(cudaMemcpyAsync(h->weights, blob, h->n_weights * sizeof(float),
                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-  if (group_pack(h->group, h->weights, s, &h->launches) || lane_pack(h->lanes, h->weights, s, &h->launches))
-    return fail("re-packing the weights for the fused engines failed");
+  if (warp_pack(h->warpeng, h->weights, s, &h->launches) ||
+      recurrent_tc_pack(h->rtc, h->net, h->weights, s, &h->launches))
+    return fail("re-packing the weights for the warp engine / the tcgen05 recurrent kernel failed");
   if (!on_device) MZ_CUDA(cudaStreamSynchronize(s));  // the host blob may be pageable and short-lived
   return 0;
 }
@@ -849,7 +895,7 @@ int mz_search(mz_handle* h, const float* obs_dev, const float* root_logits_dev, 
               const float* root_emb_dev, const uint8_t* invalid_dev, const float* noise_dev,
               const mz_search_args* args, int32_t* action_out_dev, float* action_weights_out_dev,
               float* root_value_out_dev, void* stream) {
-  if (h == nullptr) return mz::fail("mz_search: NULL handle");
+  if (h == nullptr) return mz::fail_arg("mz_search: NULL handle");
   return mz::search_device(h, obs_dev, root_logits_dev, root_value_dev, root_emb_dev, invalid_dev, noise_dev, args,
                            action_out_dev, action_weights_out_dev, root_value_out_dev, (cudaStream_t)stream);
 }
@@ -857,7 +903,7 @@ int mz_search(mz_handle* h, const float* obs_dev, const float* root_logits_dev, 
 int mz_set_peer_outputs(mz_handle* h, int32_t n, const int64_t* byte_deltas) {
   using namespace mz;
   if (h == nullptr || n < 0 || n > 7 || (n > 0 && byte_deltas == nullptr))
-    return fail("mz_set_peer_outputs: expected 0..7 byte offsets");
+    return fail_arg("mz_set_peer_outputs: expected 0..7 byte offsets");
   h->peer_deltas.assign(byte_deltas, byte_deltas + n);
   return 0;
 }
@@ -866,8 +912,8 @@ int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_h
                    const mz_search_args* args, int32_t* action_out_host, float* action_weights_out_host,
                    float* root_value_out_host, void* stream) {
   using namespace mz;
-  if (h == nullptr || obs_host == nullptr) return fail("mz_search_host: NULL argument");
-  if (action_out_host == nullptr) return fail("mz_search_host: action output is required");
+  if (h == nullptr || obs_host == nullptr) return fail_arg("mz_search_host: NULL argument");
+  if (action_out_host == nullptr) return fail_arg("mz_search_host: action output is required");
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t B = h->cfg.batch, BA = B * h->cfg.num_actions, BO = B * h->cfg.obs_dim;
@@ -888,12 +934,12 @@ int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_h
     std::memcpy(h->h_noise, noise_host, BA * sizeof(float));
     MZ_CUDA(cudaMemcpyAsync(h->d_noise, h->h_noise, BA * sizeof(float), cudaMemcpyHostToDevice, s));
   }
-  if (search_device(h, obs_in_place ? h->h_obs : h->d_obs, nullptr, nullptr, nullptr,
-                    invalid_host ? h->d_invalid : nullptr, noise_host ? h->d_noise : nullptr, args,
-                    explicit_copies ? h->d_action_out : h->h_action_out,
-                    explicit_copies ? h->d_weights_out : h->h_weights_out,
-                    explicit_copies ? h->d_value_out : h->h_value_out, s))
-    return 1;
+  if (int rc = search_device(h, obs_in_place ? h->h_obs : h->d_obs, nullptr, nullptr, nullptr,
+                             invalid_host ? h->d_invalid : nullptr, noise_host ? h->d_noise : nullptr, args,
+                             explicit_copies ? h->d_action_out : h->h_action_out,
+                             explicit_copies ? h->d_weights_out : h->h_weights_out,
+                             explicit_copies ? h->d_value_out : h->h_value_out, s))
+    return rc;
   if (explicit_copies) {
     MZ_CUDA(cudaMemcpyAsync(h->h_action_out, h->d_action_out, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     MZ_CUDA(cudaMemcpyAsync(h->h_weights_out, h->d_weights_out, BA * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -910,19 +956,20 @@ int mz_begin(mz_handle* h, const float* root_logits_dev, const float* root_value
              const uint8_t* invalid_dev, const float* noise_dev, const mz_search_args* args, void* stream) {
   using namespace mz;
   if (h == nullptr || root_logits_dev == nullptr || root_value_dev == nullptr || root_emb_dev == nullptr)
-    return fail("mz_begin: NULL argument");
-  if (check_args(h, args)) return 1;
+    return fail_arg("mz_begin: NULL argument");
+  if (int rc = check_args(h, args)) return rc;
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   if (stage_keys(h, args, (cudaStream_t)stream)) return 1;
   h->resident.dirty = false;
+  h->tree_valid = true;
   return launch_begin(h, root_logits_dev, root_value_dev, root_emb_dev, invalid_dev, noise_dev, (cudaStream_t)stream);
 }
 
 int mz_select(mz_handle* h, int32_t sim, int32_t* action_out_dev, float* parent_emb_out_dev, void* stream) {
   using namespace mz;
   if (h == nullptr || action_out_dev == nullptr || parent_emb_out_dev == nullptr)
-    return fail("mz_select: NULL argument");
-  if (sim < 0 || sim >= h->params.num_simulations) return fail("mz_select: sim out of range");
+    return fail_arg("mz_select: NULL argument");
+  if (sim < 0 || sim >= h->params.num_simulations) return fail_arg("mz_select: sim out of range");
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   SelectIO sio{h->sel_parent, h->sel_action, h->sel_next, action_out_dev, parent_emb_out_dev};
   MZ_DISPATCH_G(h, select_kernel, tree_blocks(h), (cudaStream_t)stream, h->tree, h->params, (int)sim, sio);
@@ -935,8 +982,8 @@ int mz_expand_backup(mz_handle* h, int32_t sim, const float* reward_dev, const f
   using namespace mz;
   if (h == nullptr || reward_dev == nullptr || prior_logits_dev == nullptr || value_dev == nullptr ||
       next_emb_dev == nullptr)
-    return fail("mz_expand_backup: NULL argument");
-  if (sim < 0 || sim >= h->params.num_simulations) return fail("mz_expand_backup: sim out of range");
+    return fail_arg("mz_expand_backup: NULL argument");
+  if (sim < 0 || sim >= h->params.num_simulations) return fail_arg("mz_expand_backup: sim out of range");
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   ExpandIO eio{h->sel_parent, h->sel_action, h->sel_next, reward_dev, discount_dev, value_dev, prior_logits_dev,
                next_emb_dev};
@@ -948,13 +995,15 @@ int mz_expand_backup(mz_handle* h, int32_t sim, const float* reward_dev, const f
 int mz_finish(mz_handle* h, int32_t* action_out_dev, float* action_weights_out_dev, void* stream) {
   using namespace mz;
   if (h == nullptr || action_out_dev == nullptr || action_weights_out_dev == nullptr)
-    return fail("mz_finish: NULL argument");
+    return fail_arg("mz_finish: NULL argument");
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   return launch_finish(h, action_out_dev, action_weights_out_dev, (cudaStream_t)stream);
 }
 
 int mz_get_tree(mz_handle* h, mz_tree_view* v) {
-  if (h == nullptr || v == nullptr) return mz::fail("mz_get_tree: NULL argument");
+  if (h == nullptr || v == nullptr) return mz::fail_arg("mz_get_tree: NULL argument");
+  if (!h->tree_valid)
+    return mz::fail("mz_get_tree: the last search did not keep its tree (set MZ_FLAG_WANT_TREE in mz_search_args.flags)");
   const mz::Tree& t = h->tree;
   {  // the CTA-resident engine keeps packed records; the mctx SoA view is produced when somebody asks for it
     std::string err;
@@ -982,14 +1031,14 @@ int mz_get_tree(mz_handle* h, mz_tree_view* v) {
 }
 
 int mz_launch_count(mz_handle* h, int64_t* count) {
-  if (h == nullptr || count == nullptr) return mz::fail("mz_launch_count: NULL argument");
+  if (h == nullptr || count == nullptr) return mz::fail_arg("mz_launch_count: NULL argument");
   *count = h->launches;
   return 0;
 }
 
 int mz_last_kernel_ms(mz_handle* h, float* ms) {
   using namespace mz;
-  if (h == nullptr || ms == nullptr) return fail("mz_last_kernel_ms: NULL argument");
+  if (h == nullptr || ms == nullptr) return fail_arg("mz_last_kernel_ms: NULL argument");
   if (!h->timed) return fail("no search has been timed yet");
   MZ_CUDA(cudaEventSynchronize(h->ev_stop));
   MZ_CUDA(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
@@ -998,7 +1047,7 @@ int mz_last_kernel_ms(mz_handle* h, float* ms) {
 
 int mz_math_probe(int32_t kind, const float* x_dev, float* y_dev, int64_t n, void* stream) {
   using namespace mz;
-  if (x_dev == nullptr || y_dev == nullptr || n < 0) return fail("mz_math_probe: bad argument");
+  if (x_dev == nullptr || y_dev == nullptr || n < 0) return fail_arg("mz_math_probe: bad argument");
   if (n == 0) return 0;
   math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, x_dev, y_dev, (long)n);
   MZ_CUDA(cudaGetLastError());

@@ -112,7 +112,8 @@ class MuZeroPolicy(_EnginePolicy):  # muax/policy.py:13-30
             pb_c_init=kwargs.get("pb_c_init", 1.25),
             pb_c_base=kwargs.get("pb_c_base", 19652),
             global_batch=kwargs.get("global_batch"), batch_offset=kwargs.get("batch_offset", 0),
-            engine=kwargs.get("engine", _lib.ENGINE_AUTO))
+            engine=kwargs.get("engine", _lib.ENGINE_AUTO), want_tree=kwargs.get("want_tree", False),
+            precision=kwargs.get("precision", _lib.PRECISION_FP32))
 
 
 class GumbelMuZeroPolicy(_EnginePolicy):  # muax/policy.py:33-47
@@ -127,7 +128,8 @@ class GumbelMuZeroPolicy(_EnginePolicy):  # muax/policy.py:33-47
             max_num_considered_actions=kwargs.get("max_num_considered_actions", 16),
             gumbel_scale=kwargs.get("gumbel_scale", 1),
             global_batch=kwargs.get("global_batch"), batch_offset=kwargs.get("batch_offset", 0),
-            engine=kwargs.get("engine", _lib.ENGINE_AUTO))
+            engine=kwargs.get("engine", _lib.ENGINE_AUTO), want_tree=kwargs.get("want_tree", False),
+            precision=kwargs.get("precision", _lib.PRECISION_FP32))
 
 
 class StochasticMuZeroPolicy(Policy):  # muax/policy.py:50-67 — SURVEY.md §8(f) rank 3, not built yet

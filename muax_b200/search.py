@@ -125,12 +125,13 @@ class SearchEngine:
     def make_args(self, rng_key, *, policy=_lib.POLICY_MUZERO, qtransform=None, num_simulations=5, temperature=1.0,
                   max_depth=None, dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25, pb_c_base=19652,
                   max_num_considered_actions=16, gumbel_scale=1.0, value_scale=0.1, maxvisit_init=50.0,
-                  global_batch=None, batch_offset=0, engine=_lib.ENGINE_AUTO):
+                  global_batch=None, batch_offset=0, engine=_lib.ENGINE_AUTO, want_tree=False,
+                  precision=_lib.PRECISION_FP32):
         # a 0.45 ms search makes the host call path matter: the argument struct is built once per distinct keyword
         # set and only the key words change from act to act
         ck = (policy, qtransform, num_simulations, temperature, max_depth, dirichlet_fraction, dirichlet_alpha,
               pb_c_init, pb_c_base, max_num_considered_actions, gumbel_scale, value_scale, maxvisit_init, global_batch,
-              batch_offset, engine)
+              batch_offset, engine, want_tree, precision)
         cached = self._args_cache.get(ck)
         if cached is not None:
             cached.key0, cached.key1 = key_words(rng_key)
@@ -147,6 +148,8 @@ class SearchEngine:
         a.global_batch = self.batch if global_batch is None else int(global_batch)
         a.batch_offset = int(batch_offset)
         a.engine = engine
+        a.flags = _lib.FLAG_WANT_TREE if want_tree else 0
+        a.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}.get(precision, precision)
         a.temperature, a.dirichlet_fraction, a.dirichlet_alpha = temperature, dirichlet_fraction, dirichlet_alpha
         a.pb_c_init, a.pb_c_base, a.gumbel_scale = pb_c_init, pb_c_base, gumbel_scale
         a.value_scale, a.maxvisit_init = value_scale, maxvisit_init
@@ -254,7 +257,8 @@ class SearchEngine:
 
     # ------------------------------------------------------------------ introspection
     def tree(self):
-        """Zero-copy CUDA tensor views of the last search tree (mctx.Tree field names)."""
+        """Zero-copy CUDA tensor views of the last search tree (mctx.Tree field names).  The search must have run
+        with `want_tree=True` (muax never reads `PolicyOutput.search_tree`, so `act` does not keep it by default)."""
         v = _lib.TreeView()
         _lib.check(self.lib.mz_get_tree(self._h, ctypes.byref(v)), "mz_get_tree")
         dims = {"B": v.batch, "N": v.num_nodes, "A": v.num_actions, "E": v.embed_dim}

@@ -30,7 +30,7 @@ def _engine(nets, B, cfg, num_sim, obs_dim=None):
 
 def _search_kwargs(cfg):
     kw = dict(policy=cfg.get("policy", 0), qtransform=cfg.get("qtransform", 0),
-              num_simulations=cfg["num_simulations"], max_depth=cfg.get("max_depth") or None)
+              num_simulations=cfg["num_simulations"], max_depth=cfg.get("max_depth") or None, want_tree=True)
     for k in ("temperature", "dirichlet_fraction", "dirichlet_alpha", "pb_c_init", "pb_c_base", "gumbel_scale",
               "global_batch", "batch_offset"):
         if k in cfg:
@@ -47,15 +47,15 @@ def _collect(eng, action, weights, root_value):
     return got
 
 
-ENGINES = [1, 2, 3, 4, 5, 6, 7, 8]  # MZ_ENGINE_STEPWISE, _FUSED (best available), _FUSED_CTA, _GROUP, _LANE, _LANE2, _RESIDENT, _FUSED_WARP
+ENGINES = [1, 2, 7, 8, 9]  # MZ_ENGINE_STEPWISE, _FUSED (best one-launch engine), _RESIDENT, _FUSED_WARP, _TREEWARP
 
 
 def _fused_or_skip(eng, engine_id, run):
     try:
         return run()
     except RuntimeError as e:
-        if engine_id != 1 and "fused engine" in str(e):
-            pytest.skip("fused engine does not cover this configuration")
+        if engine_id != 1 and "one-launch engine does not support" in str(e):
+            pytest.skip("this engine does not cover the configuration")
         raise
 
 
@@ -137,10 +137,9 @@ def test_seeded_batches_match_c_restatement(c_oracle, engine_id, policy, qt, A, 
 
 
 @pytest.mark.parametrize("engine_id", ENGINES)
-def test_headline_size_invariants_and_sampled_rows(c_oracle, engine_id):
+def test_headline_size_every_row(c_oracle, engine_id):
     """BASELINE.json headline shapes (CartPole nets, B=4096, num_sim=50): size-independent tree invariants on
-    every tree, and bit-exact parity on a sample of rows re-run alone through the C restatement (legal because
-    PRNG draws are indexed by global row)."""
+    every tree, and bit-exact parity of EVERY row (tree state, outputs, path depths) with the C restatement."""
     B, NS = 4096, 50
     rng = np.random.default_rng(0)
     nets = make_nets(rng, 4, 8, 2, 21)
@@ -153,9 +152,9 @@ def test_headline_size_invariants_and_sampled_rows(c_oracle, engine_id):
     got = _collect(eng, *out)
     check_tree_invariants(got, NS)
     assert np.allclose(got["action_weights"].sum(-1), 1.0, atol=1e-6)
-    for lo in (0, 1777, 4064):
-        want = c_oracle.search(nets, key, obs=obs[lo:lo + 32], global_batch=B, batch_offset=lo, **cfg)
-        assert_same_search({k: v[lo:lo + 32] for k, v in got.items() if k in OUT_FIELDS}, want)
+    want = c_oracle.search(nets, key, obs=obs, **cfg)
+    assert_same_search(got, want)
+    assert np.array_equal(got["sim_depth"], want["sim_depth"])
 
 
 @pytest.mark.parametrize("lanes,producers", [("8", "2"), ("16", "2"), ("8", "0"), ("16", "3")])
@@ -192,6 +191,44 @@ def test_warp_engine_variants(c_oracle, monkeypatch, lanes, producers, A, S, B, 
         check_tree_invariants(got, NS)
 
 
+@pytest.mark.parametrize("lanes", ["8", "16", "32"])
+@pytest.mark.parametrize("policy,qt,A,E,hidden,S,B,NS,max_depth,K", [
+    (0, 0, 4, 64, (16,), 10, 301, 60, 0, None),        # C3 stock shapes, ragged batch
+    (1, 0, 4, 64, (16,), 10, 130, 32, 0, None),        # C4: Gumbel with the qtransform MuZero.act forces
+    (1, 1, 4, 64, (64, 64, 16), 20, 77, 24, 0, None),  # notebook nets, mctx's Gumbel default qtransform
+    (0, 1, 7, 24, (20,), 5, 65, 40, 6, "3"),           # odd widths, depth limit, table cut short
+    (0, 0, 18, 32, (48, 24), 10, 33, 30, 0, "0"),      # 18 actions (one tree per warp), no table at all
+    (0, 0, 2, 8, (16,), 10, 64, 0, 0, None),           # num_simulations = 0
+])
+def test_treewarp_engine_variants(c_oracle, monkeypatch, lanes, policy, qt, A, E, hidden, S, B, NS, max_depth, K):
+    """The tree-warp engine (mz_treewarp.cu) with 8 / 16 / 32 lanes per tree (4 / 2 / 1 trees per warp) on generic
+    shapes: both policies and qtransforms, invalid actions, a depth limit (re-expansion), ragged batches (surplus tree
+    groups shadow the last tree), odd layer widths (scalar tails of the 128-bit loads), the tie-break table cut short
+    or absent (inline threefry continuation), and an empty search — bit-identical to the C restatement."""
+    monkeypatch.setenv("MZ_TREEWARP_LANES", lanes)
+    if K is not None:
+        monkeypatch.setenv("MZ_TREEWARP_K", K)
+    rng = np.random.default_rng(500 + A + E)
+    nets = make_nets(rng, 7, E, A, 2 * S + 1, hidden=hidden, bias_scale=0.05)
+    obs = rng.standard_normal((B, 7)).astype(np.float32)
+    invalid = (rng.random((B, A)) < 0.25).astype(np.uint8) if A > 2 else None
+    if invalid is not None:
+        invalid[:, 2] = 0
+    key = np.array([11, 7000 + A], np.uint32)
+    cfg = dict(policy=policy, qtransform=qt, num_simulations=NS, support_size=S)
+    if max_depth:
+        cfg["max_depth"] = max_depth
+    want = c_oracle.search(nets, key, obs=obs, invalid=invalid, **cfg)
+    eng = _engine(nets, B, cfg, max(NS, 1))
+    out = eng.search(key, obs=torch.from_numpy(obs).cuda(), invalid_actions=invalid, engine=9, **_search_kwargs(cfg))
+    got = _collect(eng, *out)
+    assert_same_search(got, want)
+    if NS > 0:
+        assert np.array_equal(got["sim_depth"], want["sim_depth"])
+    if not max_depth and NS > 0:
+        check_tree_invariants(got, NS)
+
+
 @pytest.mark.parametrize("policy,qt,A,E,H,B,NS", [(0, 0, 4, 64, (64,), 64, 16), (1, 1, 18, 64, (64, 32), 24, 12),
                                                   (0, 0, 3, 32, (48,), 9, 20)])
 def test_resident_engine_streamed_weights(c_oracle, monkeypatch, policy, qt, A, E, H, B, NS):
@@ -222,11 +259,10 @@ def test_resident_engine_streamed_weights(c_oracle, monkeypatch, policy, qt, A, 
     ("C3 LunarLander notebook 64-64-16", 8, 64, 4, 20, (64, 64, 16), 0, 4096, 200, 0),
     ("C4 Gumbel", 8, 64, 4, 10, (16,), 1, 4096, 32, 1),
     ("C5 Atari-sized heads, one GPU's shard", 256, 256, 18, 10, (256,), 1, 1024, 50, 0)])
-def test_baseline_full_sizes_on_the_resident_engine(c_oracle, name, obs_dim, E, A, S, hidden, minmax, B, NS, policy):
-    """BASELINE.json configs 2-4 at their full sizes through AUTO (= the CTA-resident engine: trees in HBM/L2, weights
-    in shared memory or streamed through the TMA ring at C5): size-independent tree invariants on every tree, and
-    bit-exact parity on sampled row blocks re-run alone through the C restatement (PRNG draws are indexed by global
-    row, so a block of rows is reproducible on its own)."""
+def test_baseline_full_sizes_every_row(c_oracle, name, obs_dim, E, A, S, hidden, minmax, B, NS, policy):
+    """BASELINE.json configs 3-5 at their full sizes through AUTO (the tree-warp engine for the LunarLander nets, the
+    CTA-resident engine with weights streamed through the TMA ring at the Atari-sized heads): size-independent tree
+    invariants on every tree and bit-exact parity of EVERY row with the C restatement."""
     rng = np.random.default_rng(17)
     nets = make_nets(rng, obs_dim, E, A, 2 * S + 1, hidden=hidden)
     obs = rng.standard_normal((B, obs_dim)).astype(np.float32)
@@ -237,9 +273,9 @@ def test_baseline_full_sizes_on_the_resident_engine(c_oracle, name, obs_dim, E, 
     got = _collect(eng, *out)
     check_tree_invariants(got, NS)
     assert np.allclose(got["action_weights"].sum(-1), 1.0, atol=1e-5)
-    for lo in (0, B // 2 + 3, B - 8):
-        want = c_oracle.search(nets, key, obs=obs[lo:lo + 8], global_batch=B, batch_offset=lo, **cfg)
-        assert_same_search({k: v[lo:lo + 8] for k, v in got.items() if k in OUT_FIELDS}, want)
+    want = c_oracle.search(nets, key, obs=obs, **cfg)
+    assert_same_search(got, want)
+    assert np.array_equal(got["sim_depth"], want["sim_depth"])
 
 
 def test_host_buffer_entry_point_equals_device_entry_point():
@@ -257,7 +293,7 @@ def test_root_supplied_by_caller():
     model = np_mctx.Model(nets, np_mctx.ExactMath(), cfg["support_size"])
     logits, value, emb = model.root_inference(inp["obs"])
     eng = _engine(nets, inp["obs"].shape[0], cfg, cfg["num_simulations"])
-    for engine_id in (1, 7):  # the engines that accept a caller-made root: stepwise and CTA-resident
+    for engine_id in (1, 7, 9):  # the engines that accept a caller-made root: stepwise, CTA-resident, tree-warp
         for root in ((logits, value, emb), (None, None, emb)):
             out = eng.search(inp["key"], root=root, noise=inp["noise"], engine=engine_id, **_search_kwargs(cfg))
             got = _collect(eng, *out)
