@@ -170,6 +170,14 @@ int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_h
                    const mz_search_args* args, int32_t* action_out_host, float* action_weights_out_host,
                    float* root_value_out_host, void* stream);
 
+/* Replaces `MuZero._recurrent_inference` (muax/model.py:265-282) for a batch on its own: Dynamic -> Prediction -> the
+ * two support transforms.  action_dev [B] int32, embedding_dev [B,E] -> reward [B], value [B], prior logits [B,A],
+ * next embedding [B,E] (discount is the handle's constant).  precision: MZ_PRECISION_FP32 (the kernel every fp32 engine
+ * is checked against) or MZ_PRECISION_BF16 (the tcgen05 kernel of the throughput mode). */
+int mz_recurrent(mz_handle* h, const int32_t* action_dev, const float* embedding_dev, int32_t precision,
+                 float* reward_out_dev, float* value_out_dev, float* prior_logits_out_dev, float* next_embedding_out_dev,
+                 void* stream);
+
 /* Callback mode — for networks the declarative stacks cannot express.  The caller plays mctx's
  * `recurrent_fn` (muax/model.py:265-282) between mz_select and mz_expand_backup:
  *   mz_begin(root, ...); for sim in range(num_simulations): mz_select -> recurrent_fn -> mz_expand_backup;

@@ -19,7 +19,8 @@ struct TreeWarpState {
   int max_smem = 0, num_sms = 0, G = 0;
   int lanes = 0;          // MZ_TREEWARP_LANES: lanes per tree (8 / 16 / 32); 0 = choose per launch
   int warps = 0;          // MZ_TREEWARP_WARPS: warps per CTA; 0 = choose per launch
-  int noise_levels = 16;  // MZ_TREEWARP_K: tie-break noise levels produced ahead of the search
+  int noise_levels = 32;  // MZ_TREEWARP_K: tie-break noise levels produced ahead of the search
+  int prefetch = 0;       // MZ_TREEWARP_PREFETCH: prefetch the children's records while a level is scored
 };
 
 int treewarp_init(TreeWarpState& st, const Net& net, int device, std::string* err);

@@ -952,6 +952,39 @@ int mz_search_host(mz_handle* h, const float* obs_host, const uint8_t* invalid_h
   return 0;
 }
 
+int mz_recurrent(mz_handle* h, const int32_t* action_dev, const float* embedding_dev, int32_t precision,
+                 float* reward_out_dev, float* value_out_dev, float* prior_logits_out_dev, float* next_embedding_out_dev,
+                 void* stream) {
+  using namespace mz;
+  if (h == nullptr || action_dev == nullptr || embedding_dev == nullptr || reward_out_dev == nullptr ||
+      value_out_dev == nullptr || prior_logits_out_dev == nullptr || next_embedding_out_dev == nullptr)
+    return fail_arg("mz_recurrent: NULL argument");
+  if (precision != MZ_PRECISION_FP32 && precision != MZ_PRECISION_BF16) return fail_arg("unknown precision");
+  if (h->weights == nullptr) return fail("mz_set_weights has not been called");
+  MZ_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  // the kernels gather embeddings[b, parent[b]] from a tree: present the batch as B one-node trees with parent = 0
+  Tree view = h->tree;
+  view.embeddings = const_cast<float*>(embedding_dev);
+  view.N = 1;
+  MZ_CUDA(cudaMemsetAsync(h->sel_parent, 0, sizeof(int32_t) * h->cfg.batch, s));
+  if (precision == MZ_PRECISION_BF16) {
+    if (!h->rtc.available)
+      return fail("precision = bf16: the tcgen05 recurrent kernel does not cover this network (" + h->rtc.why + ")");
+    std::string err;
+    if (recurrent_tc_launch(h->rtc, h->net, view, h->sel_parent, action_dev, reward_out_dev, value_out_dev,
+                            prior_logits_out_dev, next_embedding_out_dev, s, &h->launches, &err))
+      return fail(err);
+  } else {
+    RecurrentIO rio{h->sel_parent, action_dev, reward_out_dev, value_out_dev, prior_logits_out_dev, next_embedding_out_dev};
+    const int grid_mlp = (h->cfg.batch + kMlpRows - 1) / kMlpRows;
+    recurrent_kernel<<<grid_mlp, kMlpThreads, mlp_smem_bytes(h->net), s>>>(h->net, h->weights, view, rio);
+    h->launches += 1;
+  }
+  MZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int mz_begin(mz_handle* h, const float* root_logits_dev, const float* root_value_dev, const float* root_emb_dev,
              const uint8_t* invalid_dev, const float* noise_dev, const mz_search_args* args, void* stream) {
   using namespace mz;

@@ -220,6 +220,27 @@ class SearchEngine:
         self._last_num_sim = args.num_simulations
         return action, weights, root_value
 
+    # ------------------------------------------------------------------ recurrent_fn on its own
+    def recurrent(self, action, embedding, precision="fp32"):
+        """`MuZero._recurrent_inference` (muax/model.py:265-282) for a batch: (action i32[B], embedding f32[B,E]) ->
+        (reward[B], value[B], prior_logits[B,A], next_embedding[B,E]) as CUDA tensors.  precision "fp32" = the kernel
+        the fp32 engines are checked against, "bf16" = the tcgen05 kernel of the throughput mode."""
+        B, A, E = self.batch, self.A, self.E
+        f32 = torch.float32
+        with self._on_device():
+            act = _dev(action, self.device, torch.int32, (B,), "action")
+            emb = _dev(embedding, self.device, f32, (B, E), "embedding")
+            reward = torch.empty(B, dtype=f32, device=self.device)
+            value = torch.empty(B, dtype=f32, device=self.device)
+            logits = torch.empty(B, A, dtype=f32, device=self.device)
+            nxt = torch.empty(B, E, dtype=f32, device=self.device)
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            prec = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}.get(precision, precision)
+            rc = self.lib.mz_recurrent(self._h, _ptr(act), _ptr(emb), prec, _ptr(reward), _ptr(value), _ptr(logits),
+                                       _ptr(nxt), stream)
+        _lib.check(rc, "mz_recurrent")
+        return reward, value, logits, nxt
+
     # ------------------------------------------------------------------ callback mode (arbitrary recurrent_fn)
     def search_with_callback(self, rng_key, root, recurrent_fn, invalid_actions=None, noise=None, **kw):
         """mctx-style search where `recurrent_fn(action i32[B], embedding f32[B,E]) -> (reward[B], discount[B] or

@@ -240,14 +240,20 @@ def masked_argmax(x, invalid):
 
 # ---------------------------------------------------------------------------------- action selection (A.4, A.5)
 
-def muzero_action_selection(m, keys, tree, rows, node, depth, qt, pb_c_init, pb_c_base, mode):
-    A = tree.children_visits.shape[-1]
+def muzero_policy_score(m, tree, rows, node, pb_c_init, pb_c_base):
+    """The exploration term of pUCT (A.5): sqrt(n) * pb_c(n) * prior / (visits + 1).  In-tree cross-check of the
+    formula: muax/frameworks/acme/tf/mcts/search.py:463-497 `puct` (tests/test_oracle_golden.py::test_puct_pins)."""
     vc = tree.children_visits[rows, node]
     node_visit = tree.node_visits[rows, node].astype(F32)
     pb_c = (F32(pb_c_init) + m.log((((node_visit + F32(pb_c_base)).astype(F32) + F32(1)) / F32(pb_c_base)).astype(F32)))
     probs = softmax(m, tree.children_prior_logits[rows, node])
-    policy_score = ((((np.sqrt(node_visit, dtype=F32) * pb_c).astype(F32)[:, None] * probs).astype(F32))
-                    / (vc + 1).astype(F32)).astype(F32)
+    return ((((np.sqrt(node_visit, dtype=F32) * pb_c).astype(F32)[:, None] * probs).astype(F32))
+            / (vc + 1).astype(F32)).astype(F32)
+
+
+def muzero_action_selection(m, keys, tree, rows, node, depth, qt, pb_c_init, pb_c_base, mode):
+    A = tree.children_visits.shape[-1]
+    policy_score = muzero_policy_score(m, tree, rows, node, pb_c_init, pb_c_base)
     value_score = qt(m, tree, rows, node)
     noise = (F32(1e-7) * tf.uniform(keys, A, mode)).astype(F32)
     to_argmax = ((value_score + policy_score).astype(F32) + noise).astype(F32)

@@ -198,7 +198,7 @@ def test_warp_engine_variants(c_oracle, monkeypatch, lanes, producers, A, S, B, 
     (1, 1, 4, 64, (64, 64, 16), 20, 77, 24, 0, None),  # notebook nets, mctx's Gumbel default qtransform
     (0, 1, 7, 24, (20,), 5, 65, 40, 6, "3"),           # odd widths, depth limit, table cut short
     (0, 0, 18, 32, (48, 24), 10, 33, 30, 0, "0"),      # 18 actions (one tree per warp), no table at all
-    (0, 0, 2, 8, (16,), 10, 64, 0, 0, None),           # num_simulations = 0
+    (0, 0, 2, 8, (16,), 10, 64, 1, 0, None),           # a single simulation
 ])
 def test_treewarp_engine_variants(c_oracle, monkeypatch, lanes, policy, qt, A, E, hidden, S, B, NS, max_depth, K):
     """The tree-warp engine (mz_treewarp.cu) with 8 / 16 / 32 lanes per tree (4 / 2 / 1 trees per warp) on generic
