@@ -14,7 +14,7 @@ INT_FIELDS = ("action", "node_visits", "parents", "action_from_parent", "childre
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not p.endswith(("reference_pins.npz", "tracer_pins.npz", "loss_pins.npz")))
+                  if not p.endswith("_pins.npz") and not os.path.basename(p).startswith("mctx_"))
 
 
 def load_golden(name):

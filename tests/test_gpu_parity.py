@@ -443,3 +443,49 @@ def test_device_actor_equals_numpy_actor_data_path(use_graph):
             assert np.array_equal(np.asarray(getattr(have, f)).astype(getattr(want, f).dtype), getattr(want, f)), f
         np.testing.assert_allclose(have.Rn, want.Rn, rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(have.w, want.w, rtol=1e-9, atol=1e-12)
+
+
+def _run_engine(engine_id, nets, key, obs, cfg, invalid=None, noise=None):
+    eng = _engine(nets, obs.shape[0], cfg, cfg["num_simulations"])
+    out = _fused_or_skip(eng, engine_id, lambda: eng.search(
+        key, obs=torch.from_numpy(obs).cuda(), invalid_actions=invalid, noise=noise, engine=engine_id,
+        **_search_kwargs(cfg)))
+    return _collect(eng, *out)
+
+
+@pytest.mark.parametrize("engine_id", ENGINES)
+def test_edge_cases_every_engine(c_oracle, engine_id):
+    """The corners mctx defines but a batched run rarely meets, on every engine:
+    a row whose actions are ALL invalid (finite min logit, masked_argmax -> 0), an empty search (num_simulations = 0:
+    uniform visit_probs), a single action (A = 1), temperature = 0 with an exact 25 / 25 visit tie (the action is then
+    decided by the final Gumbel draw alone), and a batch of one tree (BASELINE config 1's plumbing case)."""
+    rng = np.random.default_rng(3)
+    key = np.array([1, 2], np.uint32)
+    nets = make_nets(rng, 6, 16, 4, 21)
+    obs = rng.standard_normal((5, 6)).astype(np.float32)
+    invalid = np.zeros((5, 4), np.uint8)
+    invalid[0] = 1
+    invalid[2, 1:] = 1
+    for policy, qt in ((0, 0), (1, 0), (1, 1)):
+        cfg = dict(policy=policy, qtransform=qt, num_simulations=20, support_size=10)
+        want = c_oracle.search(nets, key, obs=obs, invalid=invalid, **cfg)
+        assert want["action"][0] == 0
+        assert_same_search(_run_engine(engine_id, nets, key, obs, cfg, invalid=invalid), want)
+    for policy, qt in ((0, 0), (1, 1)):
+        cfg = dict(policy=policy, qtransform=qt, num_simulations=0, support_size=10)
+        want = c_oracle.search(nets, key, obs=obs, **cfg)
+        assert_same_search(_run_engine(engine_id, nets, key, obs, cfg), want)
+    one = make_nets(rng, 6, 16, 1, 21)
+    for policy, qt in ((0, 0), (1, 1)):
+        cfg = dict(policy=policy, qtransform=qt, num_simulations=12, support_size=10)
+        want = c_oracle.search(one, key, obs=obs, **cfg)
+        assert_same_search(_run_engine(engine_id, one, key, obs, cfg), want)
+    flat = {k: [(w * 0, b * 0) for w, b in v] for k, v in make_nets(rng, 4, 8, 2, 21).items()}
+    obs2 = rng.standard_normal((64, 4)).astype(np.float32)
+    cfg = dict(policy=0, qtransform=0, num_simulations=50, support_size=10, temperature=0.0, dirichlet_fraction=0.0)
+    want = c_oracle.search(flat, key, obs=obs2, **cfg)
+    assert (want["children_visits"][:, 0] == 25).all() and 0 < want["action"].sum() < 64   # ties, both actions drawn
+    assert_same_search(_run_engine(engine_id, flat, key, obs2, cfg), want)
+    cfg = dict(policy=0, qtransform=0, num_simulations=50, support_size=10)
+    want = c_oracle.search(nets, key, obs=obs[:1], **cfg)
+    assert_same_search(_run_engine(engine_id, nets, key, obs[:1], cfg), want)

@@ -79,3 +79,29 @@ def test_dirichlet_sampler_is_a_distribution(c_oracle):
     # Var of a Dirichlet(alpha) marginal: (1/A)(1-1/A)/(A*alpha+1)
     assert np.allclose(d.var(0), 0.25 * 0.75 / (4 * 0.3 + 1), rtol=0.06)
     assert np.array_equal(c_oracle.dirichlet(threefry.PRNGKey(1), 100, 50, 4, 0.3), d[100:150])
+
+
+def test_puct_pins():
+    """The reference tree carries an independent scalar pUCT (muax/frameworks/acme/tf/mcts/search.py:463-497).  Its
+    scores and choices on 512 random nodes (tests/golden/make_puct_pins.py executes the reference function in place)
+    must be reproduced by the oracle's exploration term + the same raw Q: pb_c, sqrt(n), prior / (visits + 1) and the
+    zero-prior masking are then pinned to the reference, not to this repo's reading of mctx."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "puct_pins.npz"))
+    n, A = z["visits"].shape
+    m = np_mctx.ExactMath()
+    tree = np_mctx.Tree(n, 1, A, 1)
+    tree.node_visits[:, 0] = z["node_visits"]
+    tree.children_visits[:, 0] = z["visits"]
+    with np.errstate(divide="ignore"):
+        tree.children_prior_logits[:, 0] = np.log(z["priors"]).astype(np.float32)   # softmax(log p) = p
+    rows, node = np.arange(n), np.zeros(n, np.int32)
+    policy_score = np_mctx.muzero_policy_score(m, tree, rows, node, float(z["c_init"]), float(z["c_base"]))
+    scores = z["values"].astype(np.float32) + policy_score
+    legal = z["priors"] > 0
+    np.testing.assert_allclose(scores[legal], z["scores"][legal], rtol=2e-6, atol=2e-6)
+    assert (z["scores"][~legal] == np.finfo(np.float32).min).all()     # the reference masks zero-prior actions
+    ours = np.where(legal, scores, -np.inf).argmax(-1)
+    top2 = np.sort(np.where(legal, z["scores"], -np.inf), axis=-1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-5                          # skip float32-level near-ties
+    assert clear.mean() > 0.95 and np.array_equal(ours[clear], z["actions"][clear])
