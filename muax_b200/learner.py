@@ -174,6 +174,19 @@ class Learner:
             self.push()
         return {"loss": loss.detach(), "lr": lr, "grad_norm": gnorm.detach()}
 
+    def restore_optimizer(self, flat):
+        """`opt|count`, `opt|mu|i`, `opt|nu|i` arrays of MuZero.save -> this learner's optimiser (leaf order = the
+        order of `self._leaves`, which is the order save() wrote them in)."""
+        n = len(self._leaves)
+        if "opt|count" not in flat or any(f"opt|mu|{i}" not in flat for i in range(n)):
+            return False
+        mu = [torch.as_tensor(flat[f"opt|mu|{i}"], device=self.device, dtype=torch.float32) for i in range(n)]
+        nu = [torch.as_tensor(flat[f"opt|nu|{i}"], device=self.device, dtype=torch.float32) for i in range(n)]
+        if any(m.shape != p.shape for m, p in zip(mu, self._leaves)):
+            return False
+        self.opt.count, self.opt.mu, self.opt.nu = int(flat["opt|count"]), mu, nu
+        return True
+
     def push(self):
         """Hands the current parameters to the acting side (`model.params`): the next `act` re-packs the weight blob."""
         self.model.params = MZNetworkParams(*[

@@ -1,7 +1,9 @@
 """`MuZero` agent object with the reference's acting interface (muax/model.py:16-179), searching on a B200.
 
-Only the acting half is accelerated: `init`, `act`, `_plan`, `_root_inference`, `_recurrent_inference` and
-parameter plumbing.  `update` (learner, muax/model.py:181-201) is out of scope for this round and raises.
+The acting half is the accelerated path: `init`, `act`, `_plan`, `_root_inference`, `_recurrent_inference` and
+parameter plumbing.  `update` (learner, muax/model.py:181-201) runs the reference's default loss and optimiser on
+torch autograd (muax_b200/learner.py); `save` / `load` / `save_load` read and write both this package's `.npz` and the
+reference's pickled `.npy` (muax/model.py:203-212, muax_b200/checkpoint.py).
 Both constructor shapes are accepted: HEAD's `MuZero(network, policy_class=...)` (model.py:43-50) and the
 released `MuZero(repr_fn, pred_fn, dy_fn, policy='muzero'|'gumbel', ...)` (frameworks/coax/model.py:101-110).
 """
@@ -9,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .nn import MZNetwork, MZNetworkParams, NetFn, NetSpec, pack_stacks
+from .nn import MZNetwork, MZNetworkParams, NetFn, NetSpec, canonical_params, pack_stacks
 from .policy import GumbelMuZeroPolicy, MuZeroPolicy, RecurrentFnOutput, RootFnOutput, resolve_qtransform
 from .random import key_words
 from .search import SearchEngine
@@ -55,6 +57,7 @@ class MuZero:
         self._weights_version = 0
         self._learner = None
         self._learner_version = -1
+        self._pending_opt = None
 
     # ------------------------------------------------------------------ parameters
     def init(self, rng_key, sample_input):  # muax/model.py:62-80
@@ -75,8 +78,25 @@ class MuZero:
 
     @params.setter
     def params(self, value):
-        self._params = MZNetworkParams(*value) if not isinstance(value, MZNetworkParams) else value
+        value = MZNetworkParams(*value) if not isinstance(value, MZNetworkParams) else value
+        if any("/~/" in mod for tree in value if tree for mod in tree):  # haiku's spelling of the reference's modules
+            value = canonical_params(value)
+        self._params = value
         self._weights_version += 1
+        if self._spec is None and self._native:
+            self._spec = self._spec_from_params(value)
+
+    def _spec_from_params(self, params):
+        """Parameters given without `init()` (a loaded checkpoint, reference params): the network spec is the three
+        module factories plus the observation width read off the Representation's first layer."""
+        rep, pred, dyn = (f.build() for f in self._fns)
+        first = (params.representation or {}).get(f"{rep.name}/linear")
+        if first is None:
+            return None
+        spec = NetSpec(rep, pred, dyn, int(np.asarray(first["w"]).shape[0]))
+        if spec.full_support_size != 2 * self._support_size + 1:
+            raise ValueError("full_support_size of the networks must equal 2 * support_size + 1")
+        return spec
 
     @property
     def optimizer_state(self):
@@ -93,29 +113,59 @@ class MuZero:
             opt = self._optimizer if isinstance(self._optimizer, Optimizer) else (
                 self._learner.opt if self._learner is not None else Optimizer())
             self._learner = Learner(self, opt=opt, device=self._device)
+            if self._pending_opt:  # a loaded checkpoint's Adam moments and schedule position
+                self._learner.restore_optimizer(self._pending_opt)
+                self._pending_opt = None
         out = self._learner.update(batch)
         self._learner_version = self._weights_version  # push() bumped it: the learner's copy is still current
         self._opt_state = self._learner.opt
         return out
 
-    def save(self, file):
-        """Parameters as a flat .npz (`<group>/<module>/<w|b>`): readable without JAX (cf. model.py:203-212)."""
+    def save(self, file, reference_format=None):
+        """Parameters + optimiser state.  Default: a flat .npz (`<group>|<module>|<w|b>`, `opt|...`) readable without
+        JAX; `reference_format=True` (or a file name ending in .npy): the reference's pickled `.npy` dict
+        (muax/model.py:203-207) through muax_b200.checkpoint, which `muax.MuZero.save_load(file, save=False)` opens."""
+        if reference_format or (reference_format is None and str(file).endswith(".npy")):
+            from .checkpoint import save_reference_checkpoint
+            return save_reference_checkpoint(file, self._params, None)
         flat = {}
         for group, tree in zip(MZNetworkParams._fields, self._params):
             for mod, leaves in (tree or {}).items():
                 for leaf, arr in leaves.items():
                     flat[f"{group}|{mod}|{leaf}"] = np.asarray(arr)
+        opt = self._opt_state
+        if opt is not None and getattr(opt, "mu", None) is not None:  # Adam moments + schedule count (learner.Optimizer)
+            flat["opt|count"] = np.asarray(opt.count, np.int64)
+            for i, (m, v) in enumerate(zip(opt.mu, opt.nu)):
+                flat[f"opt|mu|{i}"] = m.detach().cpu().numpy()
+                flat[f"opt|nu|{i}"] = v.detach().cpu().numpy()
         np.savez(file, **flat)
 
     def load(self, file):
-        if not str(file).endswith(".npz"):
-            file = f"{file}.npz"
+        """Opens this package's .npz or the reference's .npy (NumPy leaves; see muax_b200/checkpoint.py).  A freshly
+        constructed model needs no `init()` first: the network spec is rebuilt from the module factories."""
+        import os
+        name = str(file)
+        if name.endswith(".npy") or (not name.endswith(".npz") and not os.path.exists(f"{name}.npz")
+                                     and os.path.exists(f"{name}.npy")):
+            from .checkpoint import load_reference_checkpoint
+            self.params, self._opt_state = load_reference_checkpoint(name)
+            self._pending_opt = None
+            return
+        if not name.endswith(".npz"):
+            name = f"{name}.npz"
         groups = {g: {} for g in MZNetworkParams._fields}
-        with np.load(file) as z:
+        opt = {}
+        with np.load(name) as z:
             for k in z.files:
+                if k.startswith("opt|"):
+                    opt[k] = z[k]
+                    continue
                 group, mod, leaf = k.split("|")
                 groups[group].setdefault(mod, {})[leaf] = z[k]
         self.params = MZNetworkParams(**groups)
+        self._pending_opt = opt or None  # restored into the learner's optimiser on the next update()
+        self._learner = None
 
     def save_load(self, file, save=True):  # muax/model.py:203-212
         self.save(file) if save else self.load(file)

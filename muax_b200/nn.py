@@ -4,7 +4,9 @@ The reference builds `hk.Module`s inside functions that `hk.transform` later tra
 same information — layer widths, activation, min-max on/off — is carried by small declarative classes
 with the SAME constructor signatures and the SAME haiku parameter-dict layout
 (`{'representation/linear': {'w': [in,out], 'b': [out]}, ...}`), which is what the CUDA
-engine consumes.  Custom architectures subclass and override `hidden` / `normalize` / `activation`
+engine consumes.  The reference creates its `hk.Linear`s inside the parent module's `__init__`
+(muax/nn.py:63-65), for which haiku spells the path `representation/~/linear`; both spellings are accepted
+everywhere and normalised to the short one (`_canon`, `canonical_params`).  Custom architectures subclass and override `hidden` / `normalize` / `activation`
 (e.g. the LunarLander notebook's 64-64-16 stacks, examples/lunarlander.ipynb cell 2).
 """
 from typing import Callable, NamedTuple, Optional
@@ -28,6 +30,19 @@ class MZNetwork(NamedTuple):  # muax/nn.py:17-20
 
 def _haiku_name(prefix, i):
     return f"{prefix}/linear" if i == 0 else f"{prefix}/linear_{i}"
+
+
+def _canon(path):
+    """haiku module path -> this package's spelling: `representation/~/linear_1` == `representation/linear_1`."""
+    return path.replace("/~/", "/")
+
+
+def canonical_params(params):
+    """MZNetworkParams (or a 3-tuple of haiku dicts) -> MZNetworkParams with canonical module paths, leaves untouched."""
+    trees = []
+    for tree in params:
+        trees.append(None if tree is None else {_canon(mod): dict(leaves) for mod, leaves in tree.items()})
+    return MZNetworkParams(*trees)
 
 
 def _trunc_normal(rng, shape, stddev):
@@ -68,7 +83,8 @@ class Module:
         for head, dims in self.heads(in_dim):
             layers = []
             for fan_in, fan_out in zip(dims[:-1], dims[1:]):
-                p = params[_haiku_name(self.name, i)]
+                name = _haiku_name(self.name, i)
+                p = params[name] if name in params else params[name.replace("/", "/~/", 1)]  # haiku's own spelling
                 w, b = _to_numpy(p["w"]), _to_numpy(p["b"])
                 if w.shape != (fan_in, fan_out) or b.shape != (fan_out,):
                     raise ValueError(f"{_haiku_name(self.name, i)}: expected w{(fan_in, fan_out)}, got {w.shape}")

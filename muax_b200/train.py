@@ -33,12 +33,19 @@ def test(model, env, key, num_simulations, num_test_episodes=None, max_steps=Non
     B = env.batch
     alive = np.ones(B, bool)
     total = np.zeros(B)
+    on_device = hasattr(obs, "is_cuda")  # a torch vector environment (CartPoleVecTorch) steps on tensors
     for _ in range(int(max_steps or getattr(env, "MAX_STEPS", 1000))):
         key, sub = mz_random.split(key)
         a = model.act(sub, obs, obs_from_batch=True, num_simulations=num_simulations, temperature=0.0)
-        obs, r, done = env.step(np.asarray(a))
+        if on_device:
+            import torch
+            a = torch.as_tensor(np.asarray(a), device=obs.device)
+        else:
+            a = np.asarray(a)
+        obs, r, done = env.step(a)
+        r, done = (x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x) for x in (r, done))
         total += np.where(alive, r, 0.0)
-        alive &= ~np.asarray(done, bool)
+        alive &= ~done.astype(bool)
         if not alive.any():
             break
     n = B if num_test_episodes is None else min(int(num_test_episodes), B)
@@ -76,8 +83,13 @@ def fit(model, env, test_env=None, n_steps=10, gamma=0.997, alpha=0.5, buffer=No
             key, k = mz_random.split(key)
             actor.step(k)
 
+    warm_up_phases = 0
     while len(buffer) < buffer_warm_up:  # buffer warm up (train.py:148-173)
         act_phase(steps_per_iteration)
+        warm_up_phases += 1
+        if warm_up_phases > 10000:
+            raise RuntimeError(f"buffer warm-up never reached {buffer_warm_up} episodes: no episode of at least "
+                               f"k_steps = {k_steps} transitions ended in {warm_up_phases * steps_per_iteration} steps")
     for it in range(max_iterations):
         t0 = time.perf_counter()
         act_phase(steps_per_iteration)
@@ -85,6 +97,8 @@ def fit(model, env, test_env=None, n_steps=10, gamma=0.997, alpha=0.5, buffer=No
         for _ in range(num_update_per_episode):  # train.py:206-214
             batch = buffer.sample(num_trajectory=num_trajectory, sample_per_trajectory=sample_per_trajectory,
                                   k_steps=k_steps)
+            if batch is None:  # every drawn episode was shorter than k_steps + 1 (replay_buffer.py:85): draw again later
+                continue
             train_loss += float(model.update(batch)["loss"])
             training_step += 1
         rec = {"iteration": it, "training_step": training_step, "loss": train_loss / max(num_update_per_episode, 1),

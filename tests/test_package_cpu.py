@@ -134,3 +134,39 @@ def test_support_transform_helpers_roundtrip():
     assert probs.shape == (6, 21) and torch.allclose(probs.sum(-1), torch.ones(6))
     back = utils.support_to_scalar(probs, 10)
     assert torch.allclose(back, x, atol=2e-3, rtol=1e-3)
+
+
+def test_checkpoint_interop_and_load_without_init(tmp_path):
+    """muax/model.py:203-212 layout (pickled .npy of {'params', 'optimizer_state'}) both ways, haiku's `~` module
+    paths, and the reference workflow `model = MuZero(...); model.load(path)` without `init()`."""
+    import muax_b200
+    from muax_b200 import checkpoint, nn
+    net = nn.create_muzero_network(nn.Representation, nn.Prediction, nn.Dynamic, 8, 2, 21)
+    model = muax_b200.MuZero(net, policy="muzero", support_size=10)
+    params = model.init(muax_b200.random.PRNGKey(3), np.zeros((1, 4), np.float32))
+    ref_file = checkpoint.save_reference_checkpoint(tmp_path / "model_params", params)
+    assert ref_file.endswith(".npy")
+    raw = open(ref_file, "rb").read()
+    assert b"muax.nn" in raw and b"MZNetworkParams" in raw          # the class the reference's unpickler looks up
+    assert b"representation/~/linear" in raw                        # haiku's spelling on disk
+    assert "muax" not in __import__("sys").modules                  # ... and no fake module left behind
+    loaded, opt = checkpoint.load_reference_checkpoint(tmp_path / "model_params")
+    assert opt is None and isinstance(loaded, nn.MZNetworkParams)
+    for a, b in zip(params, loaded):
+        assert a.keys() == b.keys()
+        for mod in a:
+            assert np.array_equal(a[mod]["w"], b[mod]["w"]) and np.array_equal(a[mod]["b"], b[mod]["b"])
+    fresh = muax_b200.MuZero(net, policy="muzero", support_size=10)
+    fresh.load(str(tmp_path / "model_params"))                       # .npy found by name, no init()
+    assert fresh._spec is not None and fresh._spec.obs_dim == 4
+    blob_a, _ = model._spec.pack(params)
+    blob_b, _ = fresh._spec.pack(fresh.params)
+    assert np.array_equal(blob_a, blob_b)
+    model.save(tmp_path / "own")                                     # this package's .npz
+    other = muax_b200.MuZero(net, policy="muzero", support_size=10)
+    other.load(tmp_path / "own")
+    assert other._spec is not None and np.array_equal(other._spec.pack(other.params)[0], blob_a)
+    tilde = nn.MZNetworkParams(*[{k.replace("/", "/~/", 1): v for k, v in t.items()} for t in params])
+    third = muax_b200.MuZero(net, policy="muzero", support_size=10)
+    third.params = tilde                                             # reference-spelled params straight in
+    assert np.array_equal(third._spec.pack(third.params)[0], blob_a)
