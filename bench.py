@@ -6,13 +6,19 @@
 
 A "step" is one `act` over one batch of synthetic observations: root inference, `num_simulations` rounds of
 select -> recurrent_fn -> backup, and the final action draw.  Workload at N=1 = the configuration the metric
-is quoted on: CartPole-v1 MLP (obs 4, embed 8, hidden 16, A=2, support 21), batch 4096, num_sim 50.  With N>1
-every rank owns 4096 trees of a 4096*N global batch (weak scaling; PRNG draws indexed by global row) and the
-step ends with one all-gather of (action, action_weights, root_value) — the only exchange on this path.
+is quoted on: CartPole-v1 MLP (obs 4, embed 8, hidden 16, A=2, support 21), batch 4096, num_sim 50.
 
-`value`  : whole-job sims/s with observations already resident in HBM (CUDA events, max over ranks).
-`e2e`    : the same metric through the host-buffer C-ABI call `mz_search_host` (pinned H2D of the observations
-           and D2H of action/action_weights/root_value inside the timed region) — what MuZero.act does.
+N > 1 (`--scaling weak`, default): every rank owns `batch` trees of a `batch * N` global batch; `--scaling strong`:
+the global batch stays `batch` and every rank owns batch / N rows ("rows sharded 4096/G").  PRNG draws
+are indexed by global row, so any split reproduces the single-GPU result.  The only exchange on the path is one
+all-gather per act of (action_weights, root_value, action) for the shared replay buffer; nothing a rank needs to step
+its own environments depends on it, so it runs on a side stream and overlaps the NEXT act's search
+(muax_b200/sharded.py `act_async`): a timed step = search of act t + whatever of act t-1's gather is still in flight.
+
+`value`  : whole-job sims/s with observations already resident in HBM (CUDA events per step, max over ranks).
+`e2e`    : the same metric through the reference-shaped plug-in call `MuZero.act(key, obs, with_pi=True,
+           with_value=True, obs_from_batch=True)` with HOST (NumPy) observations in and NumPy results out — pinned
+           H2D / D2H and the stream sync inside the timed region; at N > 1 followed by the (synchronous) gather.
 """
 import argparse
 import json
@@ -29,7 +35,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: obs_dim, E, A, S, hidden, batch per GPU, num_sim, policy, qtransform
+    # name: obs_dim, E, A, S, hidden, batch per GPU (weak) / global batch (strong), num_sim, policy, qtransform
     "cartpole_mlp_e8_b4096_sim50": dict(obs_dim=4, E=8, A=2, S=10, hidden=(16,), batch=4096, num_sim=50, policy=0,
                                         qtransform=0, minmax=1),
     "cartpole_mlp_e8_b1024_sim50": dict(obs_dim=4, E=8, A=2, S=10, hidden=(16,), batch=1024, num_sim=50, policy=0,
@@ -41,10 +47,13 @@ WORKLOADS = {
     # examples/lunarlander.ipynb cell 2-3: 64-64-16 ELU stacks, no min-max, support 20
     "lunarlander_notebook_e64_b4096_sim200": dict(obs_dim=8, E=64, A=4, S=20, hidden=(64, 64, 16), batch=4096,
                                                   num_sim=200, policy=0, qtransform=0, minmax=0),
-    # C5 per-GPU shard: 1024 trees, A=18, E=H=256; the flat 256-wide "observation" stands in for the conv torso's
-    # output (the conv root representation runs once per act outside the search loop)
+    # C5 per-GPU shard with a flat 256-wide observation standing in for the conv torso's output
     "atari_mlp_e256_b1024_sim50": dict(obs_dim=256, E=256, A=18, S=10, hidden=(256,), batch=1024, num_sim=50,
                                        policy=0, qtransform=0, minmax=1),
+    # C5 as specified: 84x84x4 uint8 frames -> conv root representation (torch / cuDNN, once per act) -> embedding 256
+    # -> search with MLP Dynamic / Prediction heads of width 256, 18 actions; 1024 trees per GPU (8192 over 8 GPUs)
+    "atari_conv_e256_b1024_sim50": dict(obs_dim=0, E=256, A=18, S=10, hidden=(256,), batch=1024, num_sim=50, policy=0,
+                                        qtransform=0, minmax=1, conv=(84, 84, 4)),
 }
 DEFAULT_WORKLOAD = "cartpole_mlp_e8_b4096_sim50"
 
@@ -59,7 +68,9 @@ def haiku_linear(rng, fan_in, fan_out):
 
 
 def make_nets(wl, seed=0):
-    """haiku default init (w ~ TruncNormal(0, 1/sqrt(fan_in)), b = 0) — BASELINE.md §4."""
+    """haiku default init (w ~ TruncNormal(0, 1/sqrt(fan_in)), b = 0) — BASELINE.md §4.  Draw order: Representation
+    (when the workload has one), value head, policy head, next-state head, reward head — unchanged since round 1, so
+    the synthetic networks and their mean path depths are the same."""
     rng = np.random.default_rng(seed)
     E, A, F = wl["E"], wl["A"], 2 * wl["S"] + 1
 
@@ -67,8 +78,11 @@ def make_nets(wl, seed=0):
         dims = [i, *wl["hidden"], o]
         return [haiku_linear(rng, a, b) for a, b in zip(dims[:-1], dims[1:])]
 
-    return dict(repr=[haiku_linear(rng, wl["obs_dim"], E)], pred_v=mlp(E, F), pred_pi=mlp(E, A),
-                dyn_ns=mlp(E + A, E), dyn_r=mlp(E + A, F))
+    nets = {}
+    if wl["obs_dim"] > 0:
+        nets["repr"] = [haiku_linear(rng, wl["obs_dim"], E)]
+    nets.update(pred_v=mlp(E, F), pred_pi=mlp(E, A), dyn_ns=mlp(E + A, E), dyn_r=mlp(E + A, F))
+    return nets
 
 
 def bytes_per_sim(wl, mean_depth):
@@ -76,14 +90,26 @@ def bytes_per_sim(wl, mean_depth):
     return mean_depth * (56 + 24 * wl["A"]) + 8 * wl["E"] + 4 * wl["A"] + 36
 
 
-def measured_peak_hbm():
+def flops_per_sim(wl):
+    """recurrent_fn FLOPs per simulation (2 x MACs of the four heads)."""
+    E, A, F = wl["E"], wl["A"], 2 * wl["S"] + 1
+
+    def macs(i, o):
+        dims = [i, *wl["hidden"], o]
+        return sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+
+    return 2 * (macs(E + A, E) + macs(E + A, F) + macs(E, F) + macs(E, A))
+
+
+def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured"
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", 1400.0)), "measured"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, 1400.0, "fallback"
 
 
 class ClockSampler:
@@ -127,7 +153,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(wl, nets, obs, key, steps, warmup, global_batch, threads=0):
+def shard(args, wl, world):
+    """-> (rows per rank, global batch)."""
+    if args.scaling == "strong":
+        if wl["batch"] % world:
+            raise SystemExit(f"--scaling strong needs the batch ({wl['batch']}) to divide by the GPU count")
+        return wl["batch"] // world, wl["batch"]
+    return wl["batch"], wl["batch"] * world
+
+
+def common_config(args, wl, name, world):
+    """The `config` object BOTH arms print (the driver compares them key by key)."""
+    B, GB = shard(args, wl, world)
+    return {"workload": name, "batch_per_gpu": B, "global_batch": GB, "num_simulations": wl["num_sim"],
+            "num_actions": wl["A"], "embed_dim": wl["E"], "policy": "muzero" if wl["policy"] == 0 else "gumbel",
+            "parallelism": f"dp{world}", "scaling": args.scaling, "precision": args.precision}
+
+
+def root_inputs(wl, rows, seed=1):
+    """Synthetic root inputs for `rows` trees: flat observations, or (conv workload) the embeddings the search starts
+    from on the CPU arm (the conv torso is outside the search path the CPU restatement covers)."""
+    rng = np.random.default_rng(seed)
+    if wl.get("conv"):
+        return rng.random((rows, wl["E"])).astype(np.float32)
+    return rng.standard_normal((rows, wl["obs_dim"])).astype(np.float32)
+
+
+def cpu_c_port(wl, nets, x, key, steps, warmup, global_batch, threads=0):
     """Times the scalar C restatement of the reference path (oracle/mz_oracle.c) on all host cores."""
     from oracle import c_oracle
     c_oracle.build()
@@ -135,32 +187,68 @@ def cpu_reference_run(wl, nets, obs, key, steps, warmup, global_batch, threads=0
     kw = dict(policy=wl["policy"], qtransform=wl["qtransform"], num_simulations=wl["num_sim"],
               support_size=wl["S"], repr_minmax=wl["minmax"], dyn_minmax=wl["minmax"], want_tree=False,
               nthreads=threads, global_batch=global_batch)
+    if wl.get("conv"):  # root = (prior logits, value, embedding) from the NumPy model on the given embeddings
+        from oracle import np_mctx
+        m = np_mctx.ExactMath()
+        v = np_mctx.stack(m, nets["pred_v"], x, 0)
+        logits = np_mctx.stack(m, nets["pred_pi"], x, 0)
+        value = np_mctx.support_to_scalar(m, np_mctx.softmax(m, v), wl["S"])
+        run = lambda: c_oracle.search(nets, key, root=(logits, value, x), **kw)  # noqa: E731
+    else:
+        run = lambda: c_oracle.search(nets, key, obs=x, **kw)  # noqa: E731
     for _ in range(warmup):
-        c_oracle.search(nets, key, obs=obs, **kw)
+        run()
     t0 = time.perf_counter()
     for _ in range(steps):
-        c_oracle.search(nets, key, obs=obs, **kw)
+        run()
     dt = time.perf_counter() - t0
-    return obs.shape[0] * wl["num_sim"] * steps / dt, dt / steps, threads
+    return x.shape[0] * wl["num_sim"] * steps / dt, dt / steps, threads, c_oracle.build_flags()
+
+
+def cpu_numpy_batched(wl, nets, x, key, budget_s=12.0):
+    """CPU-A of BASELINE.md §3: the batched NumPy restatement (oracle/np_mctx.py, libm math + BLAS) — the same array
+    program mctx runs ([B, N, A] arrays, masked loops), the closest stand-in for "JAX on CPU".  Bounded sample: as many
+    trees of the batch as fit the time budget."""
+    from oracle import np_mctx
+    if wl.get("conv"):
+        return None
+    rows = min(x.shape[0], 256)
+    kw = dict(math=np_mctx.LibmMath(), policy=wl["policy"], qtransform=wl["qtransform"], num_simulations=wl["num_sim"],
+              support_size=wl["S"], repr_minmax=wl["minmax"], dyn_minmax=wl["minmax"])
+    t0 = time.perf_counter()
+    np_mctx.act(nets, key, obs=x[:rows], global_batch=x.shape[0], **kw)
+    dt = time.perf_counter() - t0
+    if dt < budget_s / 4 and rows < x.shape[0]:  # cheap enough: take a larger sample once
+        rows = min(x.shape[0], int(rows * budget_s / (2 * dt)))
+        t0 = time.perf_counter()
+        np_mctx.act(nets, key, obs=x[:rows], global_batch=x.shape[0], **kw)
+        dt = time.perf_counter() - t0
+    return {"value": rows * wl["num_sim"] / dt, "unit": "sims/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"one act of {rows} trees x {wl['num_sim']} simulations ({dt:.1f} s), NumPy batched restatement "
+                      f"(BLAS threads as configured by the host)"}
 
 
 def run_reference(args, wl, name):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     nets = make_nets(wl)
-    B = wl["batch"]
-    obs = np.random.default_rng(1).standard_normal((B, wl["obs_dim"])).astype(np.float32)
+    B, GB = shard(args, wl, world)
+    # bounded sample of the job: one rank's rows (the CPU arm has no ranks; its sims/s does not depend on the row count
+    # beyond filling the cores)
+    x = root_inputs(wl, B)
     key = np.array([0, 0], np.uint32)
-    value, sec, threads = cpu_reference_run(wl, nets, obs, key, args.steps, max(args.warmup, 1), B)
-    sample = f"full step: {B} trees x {wl['num_sim']} simulations per step, {args.steps} steps"
+    value, sec, threads, flags = cpu_c_port(wl, nets, x, key, args.steps, max(args.warmup, 1), GB)
+    sample = f"{B} trees x {wl['num_sim']} simulations per step, {args.steps} steps"
     line = {
         "impl": "reference", "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "batch": B, "num_simulations": wl["num_sim"],
-                   "note": "CPU restatement of the mctx path (JAX/mctx are not installable on this image); "
-                           "scalar C, one tree per task, pthreads over all host cores"},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": common_config(args, wl, name, world),
+        "details": {"note": "CPU restatement of the mctx path (JAX / mctx are not installable on this image); scalar C, "
+                            "one tree per task, pthreads over all host cores", "cc_flags": flags,
+                    "host_cpus": os.cpu_count()},
         "cpu_baseline": {"value": value, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -168,13 +256,54 @@ def run_reference(args, wl, name):
     print(json.dumps(line), flush=True)
 
 
+def build_model(wl, nets, dev):
+    """The workload's networks behind the reference-shaped API (muax_b200.MuZero)."""
+    import torch
+
+    import muax_b200
+    from muax_b200 import nn
+
+    class Pred(nn.Prediction):
+        hidden, normalize = wl["hidden"], bool(wl["minmax"])
+
+    class Dyn(nn.Dynamic):
+        hidden, normalize = wl["hidden"], bool(wl["minmax"])
+
+    class Rep(nn.Representation):
+        normalize = bool(wl["minmax"])
+
+    E, A, F = wl["E"], wl["A"], 2 * wl["S"] + 1
+    if wl.get("conv"):
+        from muax_b200.conv import ResNetRepresentation
+        torch.manual_seed(0)
+        H, W, C = wl["conv"]
+        conv = ResNetRepresentation(E, frame_channels=C, height=H, width=W).to(dev).eval()
+        network = nn.MZNetwork(conv, nn._init_prediction_func(Pred, A, F), nn._init_dynamic_func(Dyn, E, A, F))
+    else:
+        network = nn.create_muzero_network(Rep, Pred, Dyn, E, A, F)
+    model = muax_b200.MuZero(network, policy="muzero" if wl["policy"] == 0 else "gumbel", discount=0.99,
+                             support_size=wl["S"], device=dev)
+
+    def haiku(prefix, stacks):
+        out, i = {}, 0
+        for layers in stacks:
+            for w, b in layers:
+                out[f"{prefix}/linear" if i == 0 else f"{prefix}/linear_{i}"] = {"w": w, "b": b}
+                i += 1
+        return out
+
+    model.params = nn.MZNetworkParams(haiku("representation", [nets["repr"]]) if "repr" in nets else None,
+                                      haiku("prediction", [nets["pred_v"], nets["pred_pi"]]),
+                                      haiku("dynamic", [nets["dyn_ns"], nets["dyn_r"]]))
+    return model
+
+
 def run_ours(args, wl, name):
     import torch
     import torch.distributed as dist
 
     from muax_b200 import _lib
-    from muax_b200.nn import pack_stacks
-    from muax_b200.search import SearchEngine
+    from muax_b200.sharded import ShardedSearch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,38 +314,65 @@ def run_ours(args, wl, name):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, NS, A = wl["batch"], wl["num_sim"], wl["A"]
-    GB = B * world
+    B, GB = shard(args, wl, world)
+    NS, A = wl["num_sim"], wl["A"]
     nets = make_nets(wl)
-    blob, cstacks = pack_stacks(nets)
-    eng = SearchEngine(cstacks, batch=B, num_actions=A, embed_dim=wl["E"], obs_dim=wl["obs_dim"],
-                       support_size=wl["S"], max_num_simulations=NS, repr_minmax=wl["minmax"],
-                       dyn_minmax=wl["minmax"], discount=0.99, device=dev)
-    eng.set_weights(blob)
+    model = build_model(wl, nets, dev)
     engine_id = {"auto": _lib.ENGINE_AUTO, "stepwise": _lib.ENGINE_STEPWISE, "fused": _lib.ENGINE_FUSED,
                  "fused_warp": _lib.ENGINE_FUSED_WARP, "treewarp": _lib.ENGINE_TREEWARP,
                  "resident": _lib.ENGINE_RESIDENT}[args.engine]
-    obs_all = np.random.default_rng(1).standard_normal((GB, wl["obs_dim"])).astype(np.float32)
+    act_kw = dict(num_simulations=NS, engine=engine_id, precision=args.precision)
+    if wl["policy"] == 1:
+        act_kw["qtransform"] = wl["qtransform"]
+    my_rows = dict(global_batch=GB, batch_offset=rank * B)
+
+    # ---- inputs: rank r owns global rows [r * B, (r + 1) * B)
+    if wl.get("conv"):
+        H, W, C = wl["conv"]
+        obs_all = np.random.default_rng(1).integers(0, 256, (GB, H, W, C), dtype=np.uint8)
+    else:
+        obs_all = root_inputs(wl, GB)
     obs_host = np.ascontiguousarray(obs_all[rank * B:(rank + 1) * B])
     obs_dev = torch.from_numpy(obs_host).to(dev)
-    kw = dict(policy=wl["policy"], qtransform=wl["qtransform"], num_simulations=NS, global_batch=GB,
-              batch_offset=rank * B, engine=engine_id)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-    from muax_b200.sharded import ShardedSearch
-    kw_local = {k: v for k, v in kw.items() if k not in ("global_batch", "batch_offset")}
-    peer = {"auto": None, "on": True, "off": False}[os.environ.get("MZ_PEER_STORES", "off")]
-    sharded = ShardedSearch(eng.search, GB, A, writes_into_out=True, peer_stores=peer)
+
+    def search_fn(rng_key, obs_local, out=None, global_batch=None, batch_offset=0, **kw):
+        return model.act_device(rng_key, obs_local, out=out, global_batch=global_batch, batch_offset=batch_offset,
+                                **act_kw, **kw)
+
+    sharded = ShardedSearch(search_fn, GB, A, writes_into_out=True)
+
+    def engine():
+        return next(iter(model._engines.values()))[0]
+
+    pending = []
 
     def step_device(i):
-        # rows [rank*B, (rank+1)*B) of the global batch; with world > 1 this ends with the one all-gather of
-        # (action_weights, root_value, action) for the shared replay buffer — done by the search kernel's own NVLink
-        # peer stores + a cross-rank barrier when symmetric memory is available, else one NCCL all-gather
+        """act t on the main stream; the all-gather of act t - 1 starts at the same moment on the side stream and the
+        step ends when both are done (N = 1: just the search)."""
         key = np.array([0, i], np.uint32)
-        return sharded.act(key, obs_dev, **kw_local)
+        prev = pending.pop() if pending else None
+        if prev is not None:
+            prev.launch()
+        handle = sharded.act_async(key, obs_dev)
+        if prev is not None:
+            prev.wait()
+        if world > 1:
+            pending.append(handle)
+        return handle
+
+    def drain():
+        if pending:
+            h = pending.pop()
+            h.launch()
+            h.wait()
 
     def step_host(i):
         key = np.array([0, i], np.uint32)
-        return eng.search_host(key, obs_host, **kw)
+        a, pi, v = model.act(key, obs_host, with_pi=True, with_value=True, obs_from_batch=True, **act_kw, **my_rows)
+        if world > 1:  # the exchange, synchronously: results of every rank on every rank
+            sharded.gather_host(a, pi, v)
+        return a
 
     def sync_all():
         torch.cuda.synchronize()
@@ -224,20 +380,24 @@ def run_ours(args, wl, name):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(step_fn, steps, events=True):
+    def timed(step_fn, steps, events=True, tail=None):
         per_step, kernel_ms = [], []
         sync_all()
         wall0 = time.perf_counter()
-        for i in range(steps):
+        for i in range(steps + (1 if tail else 0)):
             flush.fill_(float(i))  # L2 flush between timed iterations, outside the timed events
             if events:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                step_fn(1000 + i)
+                if i < steps:
+                    step_fn(1000 + i)
+                else:
+                    tail()  # the last act's exchange
                 e1.record()
                 e1.synchronize()
                 per_step.append(e0.elapsed_time(e1))
-                kernel_ms.append(eng.last_kernel_ms())
+                if i < steps:
+                    kernel_ms.append(engine().last_kernel_ms())
             else:
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
@@ -249,12 +409,14 @@ def run_ours(args, wl, name):
 
     for i in range(max(args.warmup, 3)):
         step_device(i)
+        drain()
         step_host(i)
+    eng = engine()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count()
-    dev_ms, kern_ms, wall = timed(step_device, args.steps, events=True)
+    dev_ms, kern_ms, wall = timed(step_device, args.steps, events=True, tail=drain if world > 1 else None)
     launches = eng.launch_count() - launches0
     host_ms, _, _ = timed(step_host, args.steps, events=False)
     clocks = sampler.stop() if rank == 0 else None
@@ -263,48 +425,63 @@ def run_ours(args, wl, name):
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     dev_total_ms, host_total_ms, kern_total_ms = (float(x) for x in tot.tolist())
-    eng.search(np.array([0, 1000], np.uint32), obs=obs_dev, want_tree=True, **kw)  # untimed: the tree view for D
+    # untimed: one more search keeping its tree, for the mean selected-path depth D of the roofline formula
+    model.act_device(np.array([0, 1000], np.uint32), obs_dev, want_tree=True, **act_kw, **my_rows)
     depth = float(eng.tree()["sim_depth"].float().mean().item())
     if rank == 0:
         sims = GB * NS * args.steps
         value = sims / (dev_total_ms * 1e-3)
         e2e = sims / (host_total_ms * 1e-3)
-        peak, peak_src = measured_peak_hbm()
-        alg_bytes = B * NS * bytes_per_sim(wl, depth) + 4.0 * B * (wl["obs_dim"] + A + 2)
+        hbm_peak, tensor_peak, peak_src = measured_peaks()
         kernel_ms = kern_total_ms / args.steps
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        nets1 = make_nets(wl)
-        cpu_val, cpu_sec, threads = cpu_reference_run(wl, nets1, obs_host, np.array([0, 0], np.uint32), 3, 1, GB)
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         traffic = None
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get(name, {}).get(args.engine)
+                traffic = json.load(open(prof)).get(name, {}).get(args.engine if args.precision == "fp32" else "bf16")
             except Exception:
                 traffic = None
+        if args.precision == "bf16":
+            alg = B * NS * flops_per_sim(wl)
+            achieved = alg / (kernel_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                        "frac": achieved / tensor_peak, "traffic": traffic, "peak_source": peak_src + " (sustained bf16)",
+                        "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": alg,
+                        "note": "recurrent_fn FLOPs of one act / device time of the whole act (select + tcgen05 "
+                                "recurrent kernel + backup per simulation); the recurrent kernel's own share is in "
+                                "profiles/"}
+        else:
+            alg = B * NS * bytes_per_sim(wl, depth) + 4.0 * B * (wl["obs_dim"] + A + 2)
+            achieved = alg / (kernel_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                        "algorithmic_bytes_per_launch": alg,
+                        "note": "speed-of-data yardstick: the search is latency- / issue-bound (dependent simulations "
+                                "per tree), see DESIGN.md"}
+        x_cpu = root_inputs(wl, B)
+        cpu_val, cpu_sec, threads, flags = cpu_c_port(wl, nets, x_cpu, np.array([0, 0], np.uint32), 3, 1, GB)
         line = {
             "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "batch_per_gpu": B, "global_batch": GB, "num_simulations": NS,
-                       "num_actions": A, "embed_dim": wl["E"], "policy": "muzero" if wl["policy"] == 0 else "gumbel",
-                       "engine": args.engine, "mean_path_depth": depth, "parallelism": f"dp{world}",
-                       "exchange": sharded.exchange,
-                       "l2": "256 MB buffer written between timed steps (outside the CUDA-event window)",
-                       "timing": "CUDA events per step on the launching stream, summed, max over ranks",
-                       "wall_s_incl_flush": wall},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": common_config(args, wl, name, world),
+            "details": {"engine": args.engine, "mean_path_depth": depth, "exchange": sharded.exchange,
+                        "l2": "256 MB buffer written between timed steps (outside the CUDA-event window)",
+                        "timing": "CUDA events per step on the launching stream (the step waits for the previous "
+                                  "act's exchange), summed, plus the last exchange; max over ranks",
+                        "wall_s_incl_flush": wall},
             "e2e": {"value": e2e, "unit": "sims/s", "h2d_bytes_per_step": int(obs_host.nbytes),
                     "d2h_bytes_per_step": int(B * (4 + 4 * A + 4)), "ms_per_step": host_total_ms / args.steps,
-                    "api": "mz_search_host (host buffers -> pinned staging -> the search kernel reads the observations and "
-                           "writes action / action_weights / root_value over PCIe in place (mapped pinned memory; "
-                           "copy-engine H2D for observation batches > 256 KB) -> stream sync -> caller's buffers)"},
+                    "api": "MuZero.act(key, obs, with_pi=True, with_value=True, obs_from_batch=True): NumPy observations "
+                           "in, NumPy (action, action_weights, root_value) out, one stream sync"
+                           + ("; then the all-gather of the three arrays" if world > 1 else "")},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "search is latency-bound (50 dependent simulations per tree); see DESIGN.md"},
+            "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": "sims/s", "cores": threads, "kind": "port",
-                             "sample": f"3 full steps of {B} trees x {NS} simulations ({cpu_sec * 1e3:.0f} ms each)"},
+                             "sample": f"3 full steps of {B} trees x {NS} simulations ({cpu_sec * 1e3:.0f} ms each), "
+                                       f"scalar C port, cc flags: {flags}, host cpus: {os.cpu_count()}"},
+            "cpu_baseline_numpy": cpu_numpy_batched(wl, nets, x_cpu, np.array([0, 0], np.uint32)),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -320,6 +497,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "stepwise", "fused", "fused_warp", "treewarp", "resident"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -39,7 +39,11 @@ class MuZero:
                 raise ValueError(f"policy must be one of {sorted(_POLICIES)}, got {policy!r}") from None
         self._fns = fns
         self._native = all(isinstance(f, NetFn) for f in fns)
-        if not self._native and not all(callable(f) for f in fns):
+        # hybrid: a torch Representation (e.g. the conv torso of muax_b200.conv, run once per act at the root) in front
+        # of declarative Prediction / Dynamic stacks, which are what the search loop evaluates natively
+        self._hybrid = (not self._native and isinstance(fns.prediction_fn, NetFn) and isinstance(fns.dynamic_fn, NetFn)
+                        and callable(fns.representation_fn))
+        if not self._native and not self._hybrid and not all(callable(f) for f in fns):
             raise TypeError("network functions must be muax_b200.nn factories (native) or torch callables")
         self._policy = policy_class()
         self._optimizer = optimizer
@@ -62,10 +66,14 @@ class MuZero:
     # ------------------------------------------------------------------ parameters
     def init(self, rng_key, sample_input):  # muax/model.py:62-80
         sample_input = np.asarray(sample_input)
-        if not self._native:
+        if not self._native and not self._hybrid:
             raise TypeError("init() builds parameters for muax_b200.nn modules; torch callables own theirs")
-        rep, pred, dyn = (f.build() for f in self._fns)
-        self._spec = NetSpec(rep, pred, dyn, int(np.prod(sample_input.shape[1:])))
+        if self._hybrid:  # the torch Representation owns its parameters; Prediction / Dynamic are initialised here
+            pred, dyn = self._fns.prediction_fn.build(), self._fns.dynamic_fn.build()
+            self._spec = NetSpec(None, pred, dyn, 0)
+        else:
+            rep, pred, dyn = (f.build() for f in self._fns)
+            self._spec = NetSpec(rep, pred, dyn, int(np.prod(sample_input.shape[1:])))
         if self._spec.full_support_size != 2 * self._support_size + 1:
             raise ValueError("full_support_size of the networks must equal 2 * support_size + 1")
         k0, k1 = key_words(rng_key)
@@ -83,17 +91,20 @@ class MuZero:
             value = canonical_params(value)
         self._params = value
         self._weights_version += 1
-        if self._spec is None and self._native:
+        if self._spec is None and (self._native or self._hybrid):
             self._spec = self._spec_from_params(value)
 
     def _spec_from_params(self, params):
         """Parameters given without `init()` (a loaded checkpoint, reference params): the network spec is the three
         module factories plus the observation width read off the Representation's first layer."""
-        rep, pred, dyn = (f.build() for f in self._fns)
-        first = (params.representation or {}).get(f"{rep.name}/linear")
-        if first is None:
-            return None
-        spec = NetSpec(rep, pred, dyn, int(np.asarray(first["w"]).shape[0]))
+        if self._hybrid:
+            spec = NetSpec(None, self._fns.prediction_fn.build(), self._fns.dynamic_fn.build(), 0)
+        else:
+            rep, pred, dyn = (f.build() for f in self._fns)
+            first = (params.representation or {}).get(f"{rep.name}/linear")
+            if first is None:
+                return None
+            spec = NetSpec(rep, pred, dyn, int(np.asarray(first["w"]).shape[0]))
         if spec.full_support_size != 2 * self._support_size + 1:
             raise ValueError("full_support_size of the networks must equal 2 * support_size + 1")
         return spec
@@ -265,6 +276,18 @@ class MuZero:
                       max_depth=max_depth, qtransform=qtransform, dirichlet_fraction=dirichlet_fraction,
                       dirichlet_alpha=dirichlet_alpha, pb_c_init=pb_c_init, pb_c_base=pb_c_base, **extra)
         fast = self._native and type(self._policy) in (MuZeroPolicy, GumbelMuZeroPolicy)
+        if self._hybrid and type(self._policy) in (MuZeroPolicy, GumbelMuZeroPolicy):
+            # root Representation in torch (once per act), then the native search from root = (None, None, embedding):
+            # the library runs Prediction on the embedding and everything inside the simulation loop
+            dev = torch.device("cuda") if self._device is None else torch.device(self._device)
+            emb = self._fns.representation_fn(torch.as_tensor(obs, device=dev))
+            emb = emb.reshape(emb.shape[0], -1).to(torch.float32).contiguous()
+            engine = self._engine_for(emb.shape[0], num_simulations, params)
+            kw = self._policy._search_kwargs(kwargs)
+            action, weights, root_value = engine.search(rng_key, root=(None, None, emb), invalid_actions=invalid_actions,
+                                                        noise=extra.get("noise"), out=out, **kw)
+            from .policy import PolicyOutput
+            return PolicyOutput(action, weights, engine), root_value
         if fast and not isinstance(obs, torch.Tensor):
             # host observations: the whole act is one C-ABI call (H2D, search, D2H) — no torch on the path
             obs2 = np.ascontiguousarray(obs.reshape(obs.shape[0], -1), dtype=np.float32)

@@ -53,14 +53,49 @@ class _TreeOut(ctypes.Structure):
     )
 
 
+def _host_signature():
+    """CPU feature flags of this host + the compile flags: the library is built -march=native, so a copy that travelled
+    from another machine (the build container -> the GPU box) must be rebuilt, not executed."""
+    flags = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    import hashlib
+    return hashlib.sha1((flags + "|" + build_flags()).encode()).hexdigest()
+
+
+def build_flags():
+    """The CFLAGS line of oracle/Makefile (reported beside the CPU baseline)."""
+    for line in open(os.path.join(_HERE, "Makefile")):
+        if line.startswith("CFLAGS"):
+            return line.split("=", 1)[1].strip()
+    return "?"
+
+
 def build(force=False):
     """Compile the C restatement (gcc, -ffp-contract=off).  Building the checker is not using it."""
     src = os.path.join(_HERE, "mz_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "mz_math.h")
-    if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+    mk = os.path.join(_HERE, "Makefile")
+    sig_path = _LIB_PATH + ".host"
+    sig = _host_signature()
+    fresh = (os.path.exists(_LIB_PATH) and os.path.exists(sig_path) and open(sig_path).read() == sig
+             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(p) for p in (src, hdr, mk)))
+    if fresh and not force:
         return _LIB_PATH
-    subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    import fcntl
+    os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
+    with open(_LIB_PATH + ".lock", "w") as lock:  # torchrun ranks / xdist workers: one builds, the others wait
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if force or not (os.path.exists(sig_path) and open(sig_path).read() == sig and os.path.exists(_LIB_PATH)
+                         and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(p) for p in (src, hdr, mk))):
+            subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+            with open(sig_path, "w") as f:
+                f.write(sig)
     return _LIB_PATH
 
 

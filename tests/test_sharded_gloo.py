@@ -47,8 +47,22 @@ def _worker(rank, world, port, global_batch, policy, out_dir):
         # even shards take the flat path (outputs written straight into the all-gather send buffer)
         sh = ShardedSearch(search_fn, global_batch, 3, writes_into_out=True)
         a, w, v = sh.act(key, sh.local_rows(torch.from_numpy(obs)))
+        extra = {}
+        if global_batch % world == 0:
+            # the overlapped exchange (act_async): two acts in flight with alternating buffers, then the host-side
+            # gather the end-to-end path uses — all must reproduce the synchronous result
+            key2 = np.array([0, 12], np.uint32)
+            h1 = sh.act_async(key, sh.local_rows(torch.from_numpy(obs)))
+            h2 = sh.act_async(key2, sh.local_rows(torch.from_numpy(obs)))
+            a1, w1, v1 = (t.clone() for t in h1.wait())
+            a2, w2, v2 = (t.clone() for t in h2.wait())
+            assert torch.equal(a1, a) and torch.equal(w1, w) and torch.equal(v1, v)
+            la, lw, lv = h2.local
+            ga, gw, gv = sh.gather_host(la.numpy(), lw.numpy(), lv.numpy())
+            assert np.array_equal(ga, a2.numpy()) and np.array_equal(gw, w2.numpy()) and np.array_equal(gv, v2.numpy())
+            extra = dict(a2=a2.numpy(), w2=w2.numpy())
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), a=a.numpy(), w=w.numpy(), v=v.numpy(),
-                 offset=sh.offset, count=sh.count)
+                 offset=sh.offset, count=sh.count, **extra)
     finally:
         dist.destroy_process_group()
 
