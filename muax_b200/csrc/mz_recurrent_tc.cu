@@ -35,8 +35,10 @@ constexpr int kTcM = 128;        // rows per CTA
 constexpr int kTcKC = 32;        // k values per weight chunk (two MMAs)
 constexpr int kTcStages = 4;     // weight ring depth
 constexpr int kTcMaxSteps = 32;  // 4 heads x MZ_MAX_LAYERS
-constexpr int kTcThreads = 192;  // warps 0-3: epilogue; warp 4: MMA issuer; warp 5: TMA producer
-constexpr uint32_t kTcChunkPitch = kTcM * 16;  // bytes between the 16-byte k-chunks of the A operand
+constexpr int kTcEpiWarps = 8;   // epilogue warps: warp w reads TMEM lanes 32 * (w % 4) .. + 31, column half w / 4
+constexpr int kTcEpiThreads = 32 * kTcEpiWarps;
+constexpr int kTcThreads = kTcEpiThreads + 64;  // + warp 8: MMA issuer, warp 9: TMA producer
+constexpr uint32_t kTcChunkPitch = kTcM * 16;   // bytes between the 16-byte k-chunks of the A operand
 
 enum { kEpiHidden = 0, kEpiNextState = 1, kEpiReward = 2, kEpiValue = 3, kEpiPolicy = 4 };
 enum { kBufA = 0, kBufH0 = 1, kBufH1 = 2 };
@@ -46,6 +48,8 @@ struct TcStep {
   int32_t k16;             // K / 16 after padding
   int32_t n, npad;         // true and padded (multiple of 16) output width
   int32_t epi;
+  int32_t bias_sh;         // float offset of the layer's (zero-padded) bias in the shared-memory bias table
+  int32_t minmax;          // kEpiNextState: min_max_normalize the row
   int64_t b_off;           // bias offset (floats) in the raw fp32 blob
   int64_t img_off;         // bf16-element offset of the layer's operand image
 };
@@ -55,13 +59,16 @@ struct TcArgs {
   int32_t n_steps;
   const __nv_bfloat16* images;
   const float* raw;         // raw fp32 blob (biases)
-  const float* embeddings;  // [B][N][E]
-  const int32_t* parent;    // [B]
-  const int32_t* action;    // [B]
+  // input rows: in + row * in_row_stride (+ parent[row] * in_dim when `parent` is given: embeddings[b, parent[b]])
+  const float* in;
+  int64_t in_row_stride;
+  int32_t in_dim;           // E, or obs_dim in root mode
+  const int32_t* parent;    // [B] or null
+  const int32_t* action;    // [B] or null: one-hot(action) follows the in_dim input columns (muax/nn.py:105-108)
   float *reward, *value, *logits, *next_emb;
-  int32_t B, N, E, A, S, act_kind, dyn_minmax;
-  int32_t kx16;             // k16 of the [embedding, one-hot] operand
-  int32_t bufA_bytes, bufH_bytes, bufH1_bytes, stage_bytes, tmem_cols;  // bufH1_bytes = 0 unless a head has >= 3 layers
+  int32_t B, A, S, act_kind, out_dim;  // out_dim: width of next_emb rows (E)
+  int32_t kx16;             // k16 of the input operand
+  int32_t bufA_bytes, bufH_bytes, bufH1_bytes, stage_bytes, bias_floats, tmem_cols;  // bufH1_bytes = 0 unless a head has >= 3 layers
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -127,6 +134,28 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 consecutive fp32 columns of this thread's TMEM lane: one wait per 32 columns.
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// W columns [c0, c0 + W) of this thread's accumulator row, W = 16 or 32.
+template <int W>
+__device__ __forceinline__ void tc_ldw(uint32_t taddr, float (&v)[W]) {
+  if constexpr (W == 32) tc_ld32(taddr, v);
+  else tc_ld16(taddr, v);
+}
 __device__ __forceinline__ uint32_t tc_pack2(float lo, float hi) {
   const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits)
   return *reinterpret_cast<const uint32_t*>(&p);
@@ -141,13 +170,28 @@ __device__ __forceinline__ float tc_act(float y, int kind) {
 
 // ------------------------------------------------------------------------------------------ kernel
 
+// Epilogue helper: columns [c0, c0 + W) of the accumulator row + bias -> activation -> bf16 into the A-format buffer.
+template <int W>
+__device__ __forceinline__ void tc_epi_hidden(uint32_t trow, int c0, int n, const float* bias, int act_kind, uint32_t out_sh) {
+  float v[W];
+  tc_ldw<W>(trow + (uint32_t)c0, v);
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] = (c0 + i) < n ? tc_act(v[i] + bias[c0 + i], act_kind) : 0.0f;
+#pragma unroll
+  for (int q = 0; q < W / 8; ++q)
+    tc_sts16(out_sh + (uint32_t)(c0 / 8 + q) * kTcChunkPitch, tc_pack2(v[8 * q], v[8 * q + 1]),
+             tc_pack2(v[8 * q + 2], v[8 * q + 3]), tc_pack2(v[8 * q + 4], v[8 * q + 5]), tc_pack2(v[8 * q + 6], v[8 * q + 7]));
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   __shared__ __align__(8) uint64_t bar_full[kTcStages], bar_empty[kTcStages], bar_acc, bar_aready;
   __shared__ uint32_t tmem_base_sh;
+  __shared__ float row_lo[2][kTcM], row_hi[2][kTcM];  // partial row min / max of the two column halves
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // dynamic shared memory: A operand (embedding | one-hot, later the next state) | hidden 0 | hidden 1 | weight ring
+  // dynamic shared memory: A operand (input | one-hot, later the next state) | hidden 0 | hidden 1 | weight ring | biases
   uint8_t* stages = tc_smem + a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes;
+  float* bias_all = reinterpret_cast<float*>(stages + (size_t)kTcStages * a.stage_bytes);
   const uint32_t smem_sh = smem_u32(tc_smem);
   auto buf_sh = [&](int which) -> uint32_t {
     return smem_sh + (which == kBufA ? 0u : (uint32_t)a.bufA_bytes + (which == kBufH0 ? 0u : (uint32_t)a.bufH_bytes));
@@ -160,7 +204,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
       mbar_init(&bar_empty[i], 1);
     }
     mbar_init(&bar_acc, 1);
-    mbar_init(&bar_aready, kTcM);
+    mbar_init(&bar_aready, kTcEpiThreads);
   }
   if (warp == 0) {  // one warp allocates the accumulator columns of tensor memory (and frees them at the end)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
@@ -168,13 +212,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // every layer's bias, zero padded to npad, once per CTA: the epilogues read it from shared memory (a global load per
+  // element left every epilogue iteration waiting for L2: profiles/r02_recurrent_tc_v1_*)
+  for (int s = 0; s < a.n_steps; ++s) {
+    const float* b = a.raw + a.steps[s].b_off;
+    for (int c = tid; c < a.steps[s].npad; c += kTcThreads) bias_all[a.steps[s].bias_sh + c] = c < a.steps[s].n ? __ldg(b + c) : 0.0f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
   const int row0 = blockIdx.x * kTcM;
 
-  if (warp == 5) {
+  if (warp == kTcEpiWarps + 1) {
     // ---- TMA producer: streams every layer's operand image, chunk by chunk, through the ring
     if (lane == 0) {
       uint32_t g = 0;
@@ -191,7 +241,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
+  } else if (warp == kTcEpiWarps) {
     // ---- MMA issuer: one thread drives the tensor core
     if (lane == 0) {
       uint32_t g = 0;
@@ -220,23 +270,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
     }
     __syncwarp();
   } else {
-    // ---- epilogue warps: thread = row
-    const int r = tid;  // 0..127 = TMEM lane
+    // ---- epilogue warps: thread = (row, column half)
+    const int r = (warp & 3) * 32 + lane;  // 0..127 = TMEM lane
+    const int half = warp >> 2;            // which half of a layer's columns this thread finishes
     const int row = row0 + r;
     const bool live = row < a.B;
     const int rb = min(row, a.B - 1);
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int E = a.E;
-    {  // [embedding of the parent, one-hot(action)] -> A operand (muax/nn.py:105-108)
-      const int parent = a.parent[rb], action = a.action[rb];
-      const float* src = a.embeddings + ((size_t)rb * a.N + parent) * E;
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    {  // [input row, one-hot(action)] -> A operand (muax/nn.py:105-108); the two halves take alternate 16-byte chunks
+      const int parent = a.parent != nullptr ? a.parent[rb] : 0;
+      const int action = a.action != nullptr ? a.action[rb] : -1;
+      const int D = a.in_dim;
+      const float* src = a.in + (size_t)rb * a.in_row_stride + (size_t)parent * D;
+      const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
       const int kpad = a.kx16 * 16;
-      for (int k0 = 0; k0 < kpad; k0 += 8) {
+      for (int k0 = 8 * half; k0 < kpad; k0 += 16) {
         float v[8];
+        if (vec && live && k0 + 8 <= D) {
+          const float4 lo4 = __ldcs(reinterpret_cast<const float4*>(src + k0));
+          const float4 hi4 = __ldcs(reinterpret_cast<const float4*>(src + k0 + 4));
+          v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w; v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = k0 + i;
-          v[i] = (live && k < E) ? __ldcs(src + k) : ((live && k == E + action) ? 1.0f : 0.0f);
+          for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i;
+            v[i] = (live && k < D) ? __ldcs(src + k) : ((live && action >= 0 && k == D + action) ? 1.0f : 0.0f);
+          }
         }
         tc_sts16(buf_sh(kBufA) + (uint32_t)(k0 / 8) * kTcChunkPitch + (uint32_t)r * 16u, tc_pack2(v[0], v[1]),
                  tc_pack2(v[2], v[3]), tc_pack2(v[4], v[5]), tc_pack2(v[6], v[7]));
@@ -247,48 +306,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
     for (int s = 0; s < a.n_steps; ++s) {
       const TcStep& st = a.steps[s];
       const int n = st.n, npad = st.npad;
-      const float* bias = a.raw + st.b_off;
+      const float* bias = bias_all + st.bias_sh;
+      // this thread's columns [cb, ce): the layer's columns are split in two halves of whole 32-column groups
+      const int split = min(npad, ((npad / 2 + 31) / 32) * 32);
+      const int cb = half == 0 ? 0 : split, ce = half == 0 ? split : npad;
       tc_mbar_wait(&bar_acc, (uint32_t)(s & 1));
       tc_fence_after();
       if (st.epi == kEpiHidden) {
         const uint32_t out_sh = buf_sh(st.out_buf) + (uint32_t)r * 16u;
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-          float v[16];
-          tc_ld16(trow + (uint32_t)c0, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = c0 + i;
-            v[i] = c < n ? tc_act(v[i] + __ldg(bias + c), a.act_kind) : 0.0f;
-          }
-          tc_sts16(out_sh + (uint32_t)(c0 / 8) * kTcChunkPitch, tc_pack2(v[0], v[1]), tc_pack2(v[2], v[3]),
-                   tc_pack2(v[4], v[5]), tc_pack2(v[6], v[7]));
-          tc_sts16(out_sh + (uint32_t)(c0 / 8 + 1) * kTcChunkPitch, tc_pack2(v[8], v[9]), tc_pack2(v[10], v[11]),
-                   tc_pack2(v[12], v[13]), tc_pack2(v[14], v[15]));
-        }
+        int c0 = cb;
+        for (; c0 + 32 <= ce; c0 += 32) tc_epi_hidden<32>(trow, c0, n, bias, a.act_kind, out_sh);
+        for (; c0 < ce; c0 += 16) tc_epi_hidden<16>(trow, c0, n, bias, a.act_kind, out_sh);
       } else if (st.epi == kEpiNextState) {
         // min_max_normalize (muax/nn.py:37-44) over the row, then the new embedding: fp32 to global (expand stores it
-        // into the tree), bf16 into Prediction's A operand
+        // into the tree), bf16 into Prediction's A operand.  The two column halves of a row meet through shared memory.
         float lo = mz_inf(), hi = -mz_inf();
-        if (a.dyn_minmax) {
-          for (int c0 = 0; c0 < npad; c0 += 16) {
+        if (st.minmax) {
+          for (int c0 = cb; c0 < ce; c0 += 16) {
             float v[16];
             tc_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = c0 + i;
-              if (c < n) {
-                const float y = v[i] + __ldg(bias + c);
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < n) {
+                const float y = v[i] + bias[c0 + i];
                 lo = fminf(lo, y);
                 hi = fmaxf(hi, y);
               }
-            }
           }
+          row_lo[half][r] = lo;
+          row_hi[half][r] = hi;
+          asm volatile("bar.sync 1, %0;" ::"r"(kTcEpiThreads) : "memory");  // the epilogue warps only
+          lo = fminf(row_lo[0][r], row_lo[1][r]);
+          hi = fmaxf(row_hi[0][r], row_hi[1][r]);
         }
         float scale = hi - lo;
         if (scale < 1e-5f) scale += 1e-5f;
+        const float inv = 1.0f / scale;
         const uint32_t out_sh = buf_sh(st.out_buf) + (uint32_t)r * 16u;
-        float* dst = a.next_emb + (size_t)rb * E;
-        for (int c0 = 0; c0 < npad; c0 += 16) {
+        float* dst = a.next_emb + (size_t)rb * a.out_dim;
+        const bool dst_vec = (a.out_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(a.next_emb) & 15) == 0;
+        for (int c0 = cb; c0 < ce; c0 += 16) {
           float v[16];
           tc_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
@@ -296,11 +353,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
             const int c = c0 + i;
             float y = 0.0f;
             if (c < n) {
-              y = v[i] + __ldg(bias + c);
-              if (a.dyn_minmax) y = (y - lo) / scale;
-              if (live) dst[c] = y;
+              y = v[i] + bias[c];
+              if (st.minmax) y = (y - lo) * inv;
             }
             v[i] = y;
+          }
+          if (live) {
+            if (dst_vec && c0 + 16 <= n) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                __stcs(reinterpret_cast<float4*>(dst + c0) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < n) dst[c0 + i] = v[i];
+            }
           }
           tc_sts16(out_sh + (uint32_t)(c0 / 8) * kTcChunkPitch, tc_pack2(v[0], v[1]), tc_pack2(v[2], v[3]),
                    tc_pack2(v[4], v[5]), tc_pack2(v[6], v[7]));
@@ -308,24 +375,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
                    tc_pack2(v[12], v[13]), tc_pack2(v[14], v[15]));
         }
       } else if (st.epi == kEpiPolicy) {
-        for (int c0 = 0; c0 < npad; c0 += 16) {
+        for (int c0 = cb; c0 < ce; c0 += 16) {
           float v[16];
           tc_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int c = c0 + i;
-            if (live && c < n) a.logits[(size_t)row * a.A + c] = v[i] + __ldg(bias + c);
+            if (live && c < n) a.logits[(size_t)row * a.A + c] = v[i] + bias[c];
           }
         }
-      } else {
-        // support_to_scalar(softmax(logits)) (muax/model.py:273-274 + muax/utils.py:94-102): max, sum of exps, expectation
+      } else if (half == 0) {
+        // support_to_scalar(softmax(logits)) (muax/model.py:273-274 + muax/utils.py:94-102): max, sum of exps,
+        // expectation — a narrow row (2S + 1 logits), finished by one thread
         float mx = -mz_inf();
         for (int c0 = 0; c0 < npad; c0 += 16) {
           float v[16];
           tc_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (c0 + i < n) mx = fmaxf(mx, v[i] + __ldg(bias + c0 + i));
+            if (c0 + i < n) mx = fmaxf(mx, v[i] + bias[c0 + i]);
         }
         float sum = 0.0f;
         for (int c0 = 0; c0 < npad; c0 += 16) {
@@ -333,18 +401,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
           tc_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (c0 + i < n) sum = MZ_ADD(sum, mz_expf(MZ_SUB(v[i] + __ldg(bias + c0 + i), mx)));
+            if (c0 + i < n) sum += __expf(v[i] + bias[c0 + i] - mx);
         }
+        const float inv = 1.0f / sum;
         float x = 0.0f;
         for (int c0 = 0; c0 < npad; c0 += 16) {
           float v[16];
           tc_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (c0 + i < n) {
-              const float pr = MZ_DIV(mz_expf(MZ_SUB(v[i] + __ldg(bias + c0 + i), mx)), sum);
-              x = MZ_ADD(x, MZ_MUL((float)(c0 + i - a.S), pr));
-            }
+            if (c0 + i < n) x += (float)(c0 + i - a.S) * (__expf(v[i] + bias[c0 + i] - mx) * inv);
         }
         const float y = mz_inv_scaling(x);
         if (live) (st.epi == kEpiReward ? a.reward : a.value)[row] = y;
@@ -382,13 +448,77 @@ struct TcLayer {
   int64_t w_off, img_off;
   int K, N, kpad, npad;
 };
-struct TcImpl {
+struct TcProgram {
   TcArgs args{};
+  size_t smem = 0;
+  bool ok = false;
+};
+struct TcImpl {
+  TcProgram rec;       // recurrent_fn: reward head, next-state head, value head, policy head
+  TcProgram root_obs;  // root from observations: Representation, value head, policy head
+  TcProgram root_emb;  // root from a caller-made embedding: value head, policy head
   std::vector<TcLayer> layers;
   __nv_bfloat16* images = nullptr;
   size_t image_elems = 0;
-  size_t smem = 0;
 };
+
+struct TcHead {
+  const mz_stack* s;
+  int in, final_epi, minmax;
+};
+
+// One program = a chain of heads over a shared input operand.  Every head's first layer reads buffer A; the head
+// that ends in kEpiNextState overwrites buffer A with its (normalised) output, which the heads after it read.
+static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& heads, int in_dim, bool onehot_actions,
+                     int num_actions, size_t* img, int max_smem, std::string* why) {
+  TcArgs& a = prog.args;
+  int max_npad = 16, max_hidden_pad = 16, deepest = 1, n_steps = 0, bias_floats = 0;
+  int bufA_k = round_up(in_dim + (onehot_actions ? num_actions : 0), 16);
+  for (const TcHead& h : heads) {
+    const mz_stack& s = *h.s;
+    deepest = std::max(deepest, (int)s.n_layers);
+    for (int l = 0; l < s.n_layers; ++l) {
+      const int K = l == 0 ? h.in : s.in_dim[l], N = s.out_dim[l];
+      const int kpad = round_up(K, 16), npad = round_up(N, 16);
+      if (npad > 256) { *why = "a layer is wider than 256 units"; return false; }
+      if (n_steps >= kTcMaxSteps) { *why = "too many layers"; return false; }
+      const bool last = l == s.n_layers - 1;
+      TcStep& t = a.steps[n_steps++];
+      t.a_buf = l == 0 ? kBufA : ((l - 1) & 1 ? kBufH1 : kBufH0);
+      t.out_buf = last ? kBufA : (l & 1 ? kBufH1 : kBufH0);
+      t.k16 = kpad / 16;
+      t.n = N;
+      t.npad = npad;
+      t.epi = last ? h.final_epi : kEpiHidden;
+      t.minmax = last ? h.minmax : 0;
+      t.bias_sh = bias_floats;
+      bias_floats += npad;
+      t.b_off = s.b_off[l];
+      t.img_off = (int64_t)*img;
+      impl->layers.push_back(TcLayer{s.w_off[l], (int64_t)*img, K, N, kpad, npad});
+      *img += (size_t)kpad * npad;
+      max_npad = std::max(max_npad, npad);
+      if (!last) max_hidden_pad = std::max(max_hidden_pad, npad);
+      if (last && h.final_epi == kEpiNextState) bufA_k = std::max(bufA_k, npad);
+    }
+  }
+  a.n_steps = n_steps;
+  a.in_dim = in_dim;
+  a.kx16 = round_up(in_dim + (onehot_actions ? num_actions : 0), 16) / 16;
+  a.bufA_bytes = bufA_k / 8 * (int)kTcChunkPitch;
+  a.bufH_bytes = max_hidden_pad / 8 * (int)kTcChunkPitch;
+  a.bufH1_bytes = deepest >= 3 ? a.bufH_bytes : 0;
+  a.stage_bytes = max_npad * kTcKC * 2;
+  a.bias_floats = bias_floats;
+  int cols = 32;
+  while (cols < max_npad) cols <<= 1;
+  a.tmem_cols = cols;
+  prog.smem = (size_t)a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes + (size_t)kTcStages * a.stage_bytes +
+              (size_t)bias_floats * 4 + 128;
+  if (prog.smem > (size_t)max_smem - 2048) { *why = "operands do not fit shared memory"; return false; }
+  prog.ok = true;
+  return true;
+}
 
 int recurrent_tc_init(RecurrentTcState& st, const Net& net, int batch, int device, std::string* err) {
   (void)batch;
@@ -404,60 +534,29 @@ int recurrent_tc_init(RecurrentTcState& st, const Net& net, int batch, int devic
     return 0;
   }
   TcImpl* impl = new TcImpl();
-  TcArgs& a = impl->args;
   const int E = net.embed_dim, A = net.num_actions, F = 2 * net.support_size + 1;
-  int max_npad = 16, max_hidden_pad = 16, deepest = 1;
+  const int max_smem = (int)prop.sharedMemPerBlockOptin;
   size_t img = 0;
-  bool ok = true;
-  // heads in execution order: reward, next state, value, policy
-  struct Head { const mz_stack* s; int in, final_epi; };
-  const Head heads[4] = {{&net.dyn_r, E + A, kEpiReward}, {&net.dyn_ns, E + A, kEpiNextState},
-                         {&net.pred_v, E, kEpiValue}, {&net.pred_pi, E, kEpiPolicy}};
-  int n_steps = 0;
-  for (const Head& h : heads) {
-    const mz_stack& s = *h.s;
-    deepest = std::max(deepest, (int)s.n_layers);
-    for (int l = 0; l < s.n_layers; ++l) {
-      const int K = l == 0 ? h.in : s.in_dim[l], N = s.out_dim[l];
-      const int kpad = round_up(K, 16), npad = round_up(N, 16);
-      if (npad > 256) { ok = false; st.why = "a layer is wider than 256 units"; }
-      if (n_steps >= kTcMaxSteps) { ok = false; st.why = "too many layers"; }
-      if (!ok) break;
-      const bool last = l == s.n_layers - 1;
-      TcStep& t = a.steps[n_steps++];
-      t.a_buf = l == 0 ? kBufA : ((l - 1) & 1 ? kBufH1 : kBufH0);
-      t.out_buf = last ? kBufA : (l & 1 ? kBufH1 : kBufH0);
-      t.k16 = kpad / 16;
-      t.n = N;
-      t.npad = npad;
-      t.epi = last ? h.final_epi : kEpiHidden;
-      t.b_off = s.b_off[l];
-      t.img_off = (int64_t)img;
-      impl->layers.push_back(TcLayer{s.w_off[l], (int64_t)img, K, N, kpad, npad});
-      img += (size_t)kpad * npad;
-      max_npad = std::max(max_npad, npad);
-      if (!last) max_hidden_pad = std::max(max_hidden_pad, npad);
-    }
-    if (!ok) break;
-  }
-  if (ok && F != net.dyn_r.out_dim[net.dyn_r.n_layers - 1]) { ok = false; st.why = "support size mismatch"; }
+  bool ok = F == net.dyn_r.out_dim[net.dyn_r.n_layers - 1];
+  if (!ok) st.why = "support size mismatch";
+  // heads in execution order; the reward head runs before the next-state head overwrites their shared input
+  if (ok)
+    ok = tc_build(impl, impl->rec, {{&net.dyn_r, E + A, kEpiReward, 0}, {&net.dyn_ns, E + A, kEpiNextState, net.dyn_minmax},
+                                    {&net.pred_v, E, kEpiValue, 0}, {&net.pred_pi, E, kEpiPolicy, 0}},
+                  E, true, A, &img, max_smem, &st.why);
   if (ok) {
-    a.n_steps = n_steps;
-    a.kx16 = round_up(E + A, 16) / 16;
-    a.bufA_bytes = std::max(a.kx16 * 16, round_up(E, 16)) / 8 * (int)kTcChunkPitch;
-    a.bufH_bytes = max_hidden_pad / 8 * (int)kTcChunkPitch;
-    a.stage_bytes = max_npad * kTcKC * 2;
-    int cols = 32;
-    while (cols < max_npad) cols <<= 1;
-    a.tmem_cols = cols;
-    a.bufH1_bytes = deepest >= 3 ? a.bufH_bytes : 0;
-    impl->smem = (size_t)a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes + (size_t)kTcStages * a.stage_bytes + 128;
-    if (impl->smem > (size_t)prop.sharedMemPerBlockOptin - 1024) {
-      ok = false;
-      st.why = "operands do not fit shared memory";
-    }
+    std::string why;  // the root programs are optional: without them the root runs on the fp32 kernels
+    tc_build(impl, impl->root_emb, {{&net.pred_v, E, kEpiValue, 0}, {&net.pred_pi, E, kEpiPolicy, 0}}, E, false, A, &img,
+             max_smem, &why);
+    if (net.obs_dim > 0 && net.repr.n_layers > 0)
+      tc_build(impl, impl->root_obs, {{&net.repr, net.obs_dim, kEpiNextState, net.repr_minmax}, {&net.pred_v, E, kEpiValue, 0},
+                                      {&net.pred_pi, E, kEpiPolicy, 0}},
+               net.obs_dim, false, A, &img, max_smem, &why);
   }
-  if (ok && cudaFuncSetAttribute(recurrent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)impl->smem) != cudaSuccess) {
+  size_t smem_max = 0;
+  for (TcProgram* p : {&impl->rec, &impl->root_obs, &impl->root_emb})
+    if (p->ok) smem_max = std::max(smem_max, p->smem);
+  if (ok && cudaFuncSetAttribute(recurrent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) {
     cudaGetLastError();
     ok = false;
     st.why = "cudaFuncSetAttribute failed";
@@ -473,12 +572,14 @@ int recurrent_tc_init(RecurrentTcState& st, const Net& net, int batch, int devic
     return 0;
   }
   impl->image_elems = img;
-  a.images = impl->images;
-  a.E = E;
-  a.A = A;
-  a.S = net.support_size;
-  a.act_kind = net.activation;
-  a.dyn_minmax = net.dyn_minmax;
+  for (TcProgram* p : {&impl->rec, &impl->root_obs, &impl->root_emb}) {
+    TcArgs& a = p->args;
+    a.images = impl->images;
+    a.A = A;
+    a.S = net.support_size;
+    a.act_kind = net.activation;
+    a.out_dim = E;
+  }
   st.impl = impl;
   st.available = true;
   return 0;
@@ -505,38 +606,64 @@ int recurrent_tc_pack(RecurrentTcState& st, const Net& net, const float* raw_wei
                                                                       L.K, L.N, L.kpad, L.npad);
     *launches += 1;
   }
-  impl->args.raw = raw_weights_dev;
+  for (TcProgram* p : {&impl->rec, &impl->root_obs, &impl->root_emb}) p->args.raw = raw_weights_dev;
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-int recurrent_tc_launch(RecurrentTcState& st, const Net& net, const Tree& t, const int32_t* parent,
-                        const int32_t* action, float* reward, float* value, float* logits, float* next_emb,
-                        cudaStream_t stream, int64_t* launches, std::string* err) {
-  (void)net;
-  if (!st.available) {
-    *err = "recurrent_tc: unavailable (" + st.why + ")";
-    return 1;
-  }
-  TcImpl* impl = static_cast<TcImpl*>(st.impl);
-  TcArgs a = impl->args;
-  a.embeddings = t.embeddings;
-  a.parent = parent;
-  a.action = action;
-  a.reward = reward;
-  a.value = value;
-  a.logits = logits;
-  a.next_emb = next_emb;
-  a.B = t.B;
-  a.N = t.N;
+static int tc_run(const TcProgram& prog, TcArgs a, int B, cudaStream_t stream, int64_t* launches, std::string* err) {
+  a.B = B;
   void* args[] = {&a};
-  const int grid = (t.B + kTcM - 1) / kTcM;
-  const cudaError_t e = cudaLaunchKernel((void*)recurrent_tc_kernel, dim3(grid), dim3(kTcThreads), args, impl->smem, stream);
+  const int grid = (B + kTcM - 1) / kTcM;
+  const cudaError_t e = cudaLaunchKernel((void*)recurrent_tc_kernel, dim3(grid), dim3(kTcThreads), args, prog.smem, stream);
   *launches += 1;
   if (e != cudaSuccess) {
     *err = std::string("recurrent_tc launch failed: ") + cudaGetErrorString(e);
     return 1;
   }
   return 0;
+}
+
+int recurrent_tc_launch(RecurrentTcState& st, const Net& net, const Tree& t, const int32_t* parent,
+                        const int32_t* action, float* reward, float* value, float* logits, float* next_emb,
+                        cudaStream_t stream, int64_t* launches, std::string* err) {
+  if (!st.available) {
+    *err = "recurrent_tc: unavailable (" + st.why + ")";
+    return 1;
+  }
+  TcImpl* impl = static_cast<TcImpl*>(st.impl);
+  TcArgs a = impl->rec.args;
+  a.in = t.embeddings;
+  a.in_row_stride = (int64_t)t.N * net.embed_dim;
+  a.parent = parent;
+  a.action = action;
+  a.reward = reward;
+  a.value = value;
+  a.logits = logits;
+  a.next_emb = next_emb;
+  return tc_run(impl->rec, a, t.B, stream, launches, err);
+}
+
+bool recurrent_tc_has_root(const RecurrentTcState& st, bool from_obs) {
+  if (!st.available) return false;
+  const TcImpl* impl = static_cast<const TcImpl*>(st.impl);
+  return from_obs ? impl->root_obs.ok : impl->root_emb.ok;
+}
+
+int recurrent_tc_root(RecurrentTcState& st, const Net& net, int B, const float* obs, const float* emb_in, float* value,
+                      float* logits, float* emb_out, cudaStream_t stream, int64_t* launches, std::string* err) {
+  TcImpl* impl = static_cast<TcImpl*>(st.impl);
+  const bool from_obs = obs != nullptr;
+  const TcProgram& prog = from_obs ? impl->root_obs : impl->root_emb;
+  TcArgs a = prog.args;
+  a.in = from_obs ? obs : emb_in;
+  a.in_row_stride = from_obs ? net.obs_dim : net.embed_dim;
+  a.parent = nullptr;
+  a.action = nullptr;
+  a.reward = nullptr;
+  a.value = value;
+  a.logits = logits;
+  a.next_emb = emb_out;  // written by the Representation's epilogue (root from observations only)
+  return tc_run(prog, a, B, stream, launches, err);
 }
 
 }  // namespace mz

@@ -29,4 +29,10 @@ int recurrent_tc_launch(RecurrentTcState& st, const Net& net, const Tree& t, con
                         const int32_t* action, float* reward, float* value, float* logits, float* next_emb,
                         cudaStream_t stream, int64_t* launches, std::string* err);
 
+// `_root_inference` (muax/model.py:251-263) on the same kernel: from observations (Representation -> emb_out, value,
+// prior logits) or from a caller-made embedding (value, prior logits).  Only when recurrent_tc_has_root says so.
+bool recurrent_tc_has_root(const RecurrentTcState& st, bool from_obs);
+int recurrent_tc_root(RecurrentTcState& st, const Net& net, int B, const float* obs, const float* emb_in, float* value,
+                      float* logits, float* emb_out, cudaStream_t stream, int64_t* launches, std::string* err);
+
 }  // namespace mz

@@ -21,6 +21,7 @@ struct TreeWarpState {
   int warps = 0;          // MZ_TREEWARP_WARPS: warps per CTA; 0 = choose per launch
   int noise_levels = 32;  // MZ_TREEWARP_K: tie-break noise levels produced ahead of the search
   int prefetch = 0;       // MZ_TREEWARP_PREFETCH: prefetch the children's records while a level is scored
+  void* batched = nullptr;  // state of the per-simulation kernels (throughput mode)
 };
 
 int treewarp_init(TreeWarpState& st, const Net& net, int device, std::string* err);
@@ -32,5 +33,19 @@ int treewarp_launch(TreeWarpState& st, ResidentState& rs, const Net& net, const 
                     const float* root_value, const uint8_t* invalid, const float* noise, int32_t* action_out,
                     float* weights_out, float* root_value_out, cudaStream_t stream, int64_t* launches,
                     std::string* err);
+
+// Throughput mode (precision = bf16): the same walks as separate launches per simulation around the tcgen05 recurrent
+// kernel.  begin (policy prologue + tree init; `sel5` = 5 x B ints of scratch: parent, action, next, depth, fresh — the
+// first two feed the recurrent kernel), then per simulation select -> [recurrent] -> backup, then finish.
+int treewarp_batched_begin(TreeWarpState& st, ResidentState& rs, const Tree& tree, const SearchParams& p,
+                           const float* root_logits, const float* root_value, const float* root_emb,
+                           const uint8_t* invalid, const float* noise, int32_t* sel5, cudaStream_t stream,
+                           int64_t* launches, std::string* err);
+int treewarp_batched_select(TreeWarpState& st, int sim, cudaStream_t stream, int64_t* launches, std::string* err);
+int treewarp_batched_backup(TreeWarpState& st, const float* reward, const float* value, const float* logits,
+                            const float* next_emb, cudaStream_t stream, int64_t* launches, std::string* err);
+int treewarp_batched_finish(TreeWarpState& st, int32_t* action_out, float* weights_out, cudaStream_t stream,
+                            int64_t* launches, std::string* err);
+void treewarp_destroy(TreeWarpState& st);
 
 }  // namespace mz

@@ -311,6 +311,7 @@ struct mz_handle {
   size_t n_weights = 0;
   // scratch
   int32_t *sel_parent = nullptr, *sel_action = nullptr, *sel_next = nullptr;
+  int32_t* sel5 = nullptr;  // 5 x B scratch of the batched tree-warp kernels (throughput mode)
   float *rec_reward = nullptr, *rec_value = nullptr, *rec_logits = nullptr, *rec_emb = nullptr;
   float *root_logits = nullptr, *root_value = nullptr, *root_emb = nullptr;
   uint32_t* sim_keys_dev = nullptr;
@@ -553,7 +554,55 @@ static int launch_root(mz_handle* h, const float* obs, const float* emb_in, cuda
   return 0;
 }
 
-// Throughput mode: the stepwise tree kernels around the tcgen05 recurrent kernel.
+// Throughput mode (precision = bf16): per simulation  select -> tcgen05 recurrent kernel -> expand + backup  as three
+// launches.  The tree phases are the tree-warp engine's walks on packed records (mz_treewarp.cu: warp-uniform level
+// loop, tie-break noise from the pre-pass table, parallel backup); the root runs on the tensor-core kernel too.
+static int search_tc(mz_handle* h, const float* obs, const float* root_logits, const float* root_value,
+                     const float* root_emb, const uint8_t* invalid, const float* noise, int32_t* action_out,
+                     float* weights_out, float* root_value_out, cudaStream_t stream) {
+  if (h->weights == nullptr) return fail("mz_set_weights has not been called");
+  if (!h->rtc.available)
+    return fail("precision = bf16: the tcgen05 recurrent kernel does not cover this network (" + h->rtc.why + ")");
+  if (!h->treewarp.available) return fail("precision = bf16: the tree-warp kernels are unavailable on this device");
+  if (h->params.num_simulations + 1 >= 0xFFFF) return fail("precision = bf16: at most 65533 simulations");
+  std::string err;
+  const int NS = h->params.num_simulations;
+  if (obs != nullptr || root_logits == nullptr) {  // Prediction (and Representation) run in the library
+    const bool from_obs = obs != nullptr;
+    if (recurrent_tc_has_root(h->rtc, from_obs)) {
+      if (recurrent_tc_root(h->rtc, h->net, h->cfg.batch, obs, root_emb, h->root_value, h->root_logits, h->root_emb,
+                            stream, &h->launches, &err))
+        return fail(err);
+      if (from_obs) root_emb = h->root_emb;  // the caller's embedding is used where it lies
+    } else {
+      if (launch_root(h, obs, from_obs ? nullptr : root_emb, stream)) return 1;
+      root_emb = h->root_emb;
+    }
+    root_logits = h->root_logits;
+    root_value = h->root_value;
+  }
+  if (root_value_out != nullptr)
+    MZ_CUDA(cudaMemcpyAsync(root_value_out, root_value, sizeof(float) * h->cfg.batch, cudaMemcpyDefault, stream));
+  if (ensure_device_keys(h, stream)) return 1;
+  if (treewarp_batched_begin(h->treewarp, h->resident, h->tree, h->params, root_logits, root_value, root_emb, invalid,
+                             noise, h->sel5, stream, &h->launches, &err))
+    return fail(err);
+  const int B = h->cfg.batch;
+  for (int sim = 0; sim < NS; ++sim) {
+    if (treewarp_batched_select(h->treewarp, sim, stream, &h->launches, &err)) return fail(err);
+    if (recurrent_tc_launch(h->rtc, h->net, h->tree, h->sel5, h->sel5 + B, h->rec_reward, h->rec_value, h->rec_logits,
+                            h->rec_emb, stream, &h->launches, &err))
+      return fail(err);
+    if (treewarp_batched_backup(h->treewarp, h->rec_reward, h->rec_value, h->rec_logits, h->rec_emb, stream,
+                                &h->launches, &err))
+      return fail(err);
+  }
+  if (treewarp_batched_finish(h->treewarp, action_out, weights_out, stream, &h->launches, &err)) return fail(err);
+  return 0;
+}
+
+// Callback-free stepwise loop with the tcgen05 recurrent kernel between the generic SoA tree kernels (kept as the
+// cross-check of search_tc: MZ_ENGINE_STEPWISE + precision = bf16).
 static int run_stepwise_tc(mz_handle* h, cudaStream_t stream) {
   if (!h->rtc.available)
     return fail("precision = bf16: the tcgen05 recurrent kernel does not cover this network (" + h->rtc.why + ")");
@@ -622,10 +671,20 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   const bool treewarp_ok = have_w && treewarp_supported(h->treewarp, h->net, B, NS, h->params.max_depth);
   const bool resident_ok = have_w && resident_supported(h->resident, h->net, B, NS);
   if (args->precision == MZ_PRECISION_BF16) {
-    // throughput mode: the stepwise kernels around the tcgen05 recurrent kernel (mz_recurrent_tc.cu)
+    // throughput mode: tree-warp select / backup kernels around the tcgen05 recurrent kernel (search_tc); STEPWISE
+    // keeps the generic SoA tree kernels around the same recurrent kernel
     if (engine != MZ_ENGINE_AUTO && engine != MZ_ENGINE_STEPWISE)
-      return fail_arg("precision = bf16 runs on the stepwise engine (engine must be AUTO or STEPWISE)");
-    engine = MZ_ENGINE_STEPWISE;
+      return fail_arg("precision = bf16: engine must be AUTO or STEPWISE");
+    if (engine == MZ_ENGINE_AUTO) {
+      h->has_invalid = invalid != nullptr;
+      if (int rc = search_tc(h, obs, root_logits, root_value, root_emb, invalid, noise, action_out, weights_out,
+                             root_value_out, stream))
+        return rc;
+      h->tree_valid = true;  // records, unpacked lazily by mz_get_tree
+      MZ_CUDA(cudaEventRecord(h->ev_stop, stream));
+      h->timed = true;
+      return 0;
+    }
   }
   // AUTO: the warp engine when its compile-time shapes match and the trees fit on chip; else the tree-warp engine
   // (weights in shared memory, trees as records in L1/L2); else the CTA-resident engine (weights streamed); the
@@ -807,6 +866,7 @@ int mz_create(mz_handle** out, const mz_config* cfg) {
   MZ_TRY(dev_alloc(h, &h->sel_parent, B));
   MZ_TRY(dev_alloc(h, &h->sel_action, B));
   MZ_TRY(dev_alloc(h, &h->sel_next, B));
+  MZ_TRY(dev_alloc(h, &h->sel5, 5 * B));
   MZ_TRY(dev_alloc(h, &h->rec_reward, B));
   MZ_TRY(dev_alloc(h, &h->rec_value, B));
   MZ_TRY(dev_alloc(h, &h->rec_logits, BA));
@@ -859,6 +919,7 @@ int mz_destroy(mz_handle* h) {
   cudaDeviceSynchronize();
   mz::warp_destroy(h->warpeng);
   mz::resident_destroy(h->resident);
+  mz::treewarp_destroy(h->treewarp);
   mz::recurrent_tc_destroy(h->rtc);
   for (void* p : h->allocs) cudaFree(p);
   if (h->weights) cudaFree(h->weights);

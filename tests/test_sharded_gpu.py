@@ -1,4 +1,5 @@
-"""Two-GPU check of the sharded act (needs >= 2 GPUs, skipped otherwise): the search kernel's own NVLink peer stores +
+"""Multi-GPU check of the sharded act (2, 4 or 8 GPUs — whatever the box has; skipped on one): the overlapped exchange
+(`act_async`: NCCL all-gather on a side stream), and the search kernel's own NVLink peer stores +
 symmetric-memory barrier (`ShardedSearch(peer_stores=True)`) must deliver exactly what the NCCL all-gather path
 delivers, act after act, and both must equal the single-GPU search of the whole batch (PRNG draws are indexed by
 global row)."""
@@ -49,6 +50,17 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         res[name] = [[t.cpu().numpy() for t in o] for o in outs]
         res[name + "_exchange"] = sh.exchange
+    # the overlapped exchange: act t + 1 is issued before act t's all-gather (side stream) is waited for
+    sh = ShardedSearch(eng.search, GB, A, writes_into_out=True)
+    handles, outs = [], []
+    for step in range(5):
+        handles.append(sh.act_async(np.array([7, step], np.uint32), obs_local, num_simulations=NS))
+        if len(handles) == 2:
+            outs.append([t.clone() for t in handles.pop(0).wait()])
+    outs.append([t.clone() for t in handles.pop(0).wait()])
+    torch.cuda.synchronize()
+    res["async"] = [[t.cpu().numpy() for t in o] for o in outs]
+    res["async_exchange"] = sh.exchange
     if rank == 0:
         full = engine(GB)
         ref = []
@@ -56,10 +68,10 @@ def _worker(rank, world, port, out_dir):
             a, w, v = full.search(np.array([7, step], np.uint32), obs=torch.from_numpy(obs).cuda(), num_simulations=NS)
             torch.cuda.synchronize()
             ref.append([t.cpu().numpy() for t in (a, w, v)])
-        ok = all(np.array_equal(x, y) and np.array_equal(x, z)
-                 for p, q, r in zip(res["peer"], res["nccl"], ref) for x, y, z in zip(p, q, r))
+        ok = all(np.array_equal(x, y) and np.array_equal(x, z) and np.array_equal(x, u)
+                 for p, q, r, s in zip(res["peer"], res["nccl"], ref, res["async"]) for x, y, z, u in zip(p, q, r, s))
         with open(os.path.join(out_dir, "result.txt"), "w") as f:
-            f.write(f"{int(ok)}|{res['peer_exchange']}|{res['nccl_exchange']}")
+            f.write(f"{int(ok)}|{res['peer_exchange']}|{res['nccl_exchange']}|{res['async_exchange']}")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -69,8 +81,10 @@ def test_peer_stores_equal_nccl_all_gather_and_the_single_gpu_search(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, 29533, str(tmp_path)), nprocs=2, join=True)
-    ok, peer_exchange, nccl_exchange = open(tmp_path / "result.txt").read().split("|")
+    world = 8 if torch.cuda.device_count() >= 8 else (4 if torch.cuda.device_count() >= 4 else 2)
+    mp.spawn(_worker, args=(world, 29533, str(tmp_path)), nprocs=world, join=True)
+    ok, peer_exchange, nccl_exchange, async_exchange = open(tmp_path / "result.txt").read().split("|")
     assert peer_exchange.startswith("peer stores"), peer_exchange
     assert nccl_exchange.startswith("nccl"), nccl_exchange
+    assert "side stream" in async_exchange, async_exchange
     assert ok == "1"
