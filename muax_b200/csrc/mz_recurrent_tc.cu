@@ -8,8 +8,9 @@
 //     core matrices, offset(row, k) = (k / 8) * 2048 + row * 16 + (k % 8) * 2 — which is exactly what a "thread = row"
 //     epilogue writes without bank conflicts (a warp stores 32 consecutive 16-byte rows);
 //   * B operand (weights, W^T, K-major): packed ONCE per mz_set_weights into the same layout, bf16, zero padded to
-//     multiples of 16, cut into chunks of kTcKC k-values that one `cp.async.bulk` (TMA) each brings into a ring of
-//     kTcStages shared-memory stages (full / empty mbarriers; the ring runs ahead across layer boundaries);
+//     multiples of 16, cut into chunks of as many k-values as fit a 16 KB stage (32 at N = 256, a whole narrow layer)
+//     that one `cp.async.bulk` (TMA) each brings into a ring of up to 8 shared-memory stages (full / empty mbarriers;
+//     the ring runs ahead across layer boundaries);
 //   * D: fp32 accumulators in tensor memory, `tcgen05.mma.cta_group::1.kind::f16` M = 128, N = layer width (<= 256),
 //     K = 16 per instruction, issued by ONE thread; completion reaches the epilogue through `tcgen05.commit` on an
 //     mbarrier;
@@ -27,13 +28,15 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <vector>
 
 namespace mz {
 
 constexpr int kTcM = 128;        // rows per CTA
-constexpr int kTcKC = 32;        // k values per weight chunk (two MMAs)
-constexpr int kTcStages = 4;     // weight ring depth
+constexpr int kTcStageBytes = 16384;  // one stage of the weight ring: a layer is cut into chunks of as many k values
+                                      // (a multiple of 16) as fit — 32 at N = 256, the whole layer for narrow ones
+constexpr int kTcMaxStages = 8;  // weight ring depth: as many stages (2 .. 8) as shared memory has room for
 constexpr int kTcMaxSteps = 32;  // 4 heads x MZ_MAX_LAYERS
 constexpr int kTcEpiWarps = 8;   // epilogue warps: warp w reads TMEM lanes 32 * (w % 4) .. + 31, column half w / 4
 constexpr int kTcEpiThreads = 32 * kTcEpiWarps;
@@ -46,6 +49,7 @@ enum { kBufA = 0, kBufH0 = 1, kBufH1 = 2 };
 struct TcStep {
   int32_t a_buf, out_buf;  // A operand of the GEMM / buffer the epilogue writes (hidden and next-state steps)
   int32_t k16;             // K / 16 after padding
+  int32_t kc;              // k values per weight chunk (multiple of 16): kc * npad * 2 bytes <= kTcStageBytes
   int32_t n, npad;         // true and padded (multiple of 16) output width
   int32_t epi;
   int32_t bias_sh;         // float offset of the layer's (zero-padded) bias in the shared-memory bias table
@@ -58,7 +62,7 @@ struct TcArgs {
   TcStep steps[kTcMaxSteps];
   int32_t n_steps;
   const __nv_bfloat16* images;
-  const float* raw;         // raw fp32 blob (biases)
+  const float* bias_table;  // every step's bias, zero padded to npad, in step order (built by recurrent_tc_pack)
   // input rows: in + row * in_row_stride (+ parent[row] * in_dim when `parent` is given: embeddings[b, parent[b]])
   const float* in;
   int64_t in_row_stride;
@@ -68,7 +72,7 @@ struct TcArgs {
   float *reward, *value, *logits, *next_emb;
   int32_t B, A, S, act_kind, out_dim;  // out_dim: width of next_emb rows (E)
   int32_t kx16;             // k16 of the input operand
-  int32_t bufA_bytes, bufH_bytes, bufH1_bytes, stage_bytes, bias_floats, tmem_cols;  // bufH1_bytes = 0 unless a head has >= 3 layers
+  int32_t bufA_bytes, bufH_bytes, bufH1_bytes, stage_bytes, n_stages, bias_floats, tmem_cols;  // bufH1_bytes = 0 unless a head has >= 3 layers
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -163,35 +167,108 @@ __device__ __forceinline__ uint32_t tc_pack2(float lo, float hi) {
 __device__ __forceinline__ void tc_sts16(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ float tc_act(float y, int kind) {
-  if (kind == MZ_ACT_ELU) return y > 0.0f ? y : __expf(y) - 1.0f;
-  return y > 0.0f ? y : 0.0f;
+__device__ __forceinline__ float tc_ex2(float x) {  // 2^x on the SFU (flush-to-zero: inputs here are <= 0 or bounded)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kTcLog2e = 1.4426950408889634f;
+// ELU / ReLU of W independent units, branch-free: a `y > 0 ? y : expf(y) - 1` per unit compiles to one divergent
+// branch per element (BSSY / BSYNC around a dependent LDS -> FADD -> MUFU chain: 140 cycles per element, 19 k cycles
+// per 256-wide layer — profiles/r02_recurrent_tc_timeline.txt); here the exponential runs on every unit and a select
+// picks the result.
+template <int W>
+__device__ __forceinline__ void tc_activate(float (&v)[W], int kind) {
+  if (kind == MZ_ACT_ELU) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const float e = tc_ex2(fminf(v[i], 0.0f) * kTcLog2e) - 1.0f;
+      v[i] = v[i] > 0.0f ? v[i] : e;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = fmaxf(v[i], 0.0f);
+  }
+}
+// v[i] += bias[c0 + i] with 128-bit shared-memory loads (the bias rows are zero padded to npad and 64-byte aligned).
+template <int W>
+__device__ __forceinline__ void tc_add_bias(float (&v)[W], const float* bias, int c0) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+#pragma unroll
+  for (int q = 0; q < W / 4; ++q) {
+    const float4 b = b4[q];
+    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ kernel
 
 // Epilogue helper: columns [c0, c0 + W) of the accumulator row + bias -> activation -> bf16 into the A-format buffer.
+// Padded columns need no mask: their weights and bias are zero, and both activations map 0 to 0.
 template <int W>
-__device__ __forceinline__ void tc_epi_hidden(uint32_t trow, int c0, int n, const float* bias, int act_kind, uint32_t out_sh) {
+__device__ __forceinline__ void tc_epi_hidden(uint32_t trow, int c0, const float* bias, int act_kind, uint32_t out_sh) {
   float v[W];
   tc_ldw<W>(trow + (uint32_t)c0, v);
-#pragma unroll
-  for (int i = 0; i < W; ++i) v[i] = (c0 + i) < n ? tc_act(v[i] + bias[c0 + i], act_kind) : 0.0f;
+  tc_add_bias<W>(v, bias, c0);
+  tc_activate<W>(v, act_kind);
 #pragma unroll
   for (int q = 0; q < W / 8; ++q)
     tc_sts16(out_sh + (uint32_t)(c0 / 8 + q) * kTcChunkPitch, tc_pack2(v[8 * q], v[8 * q + 1]),
              tc_pack2(v[8 * q + 2], v[8 * q + 3]), tc_pack2(v[8 * q + 4], v[8 * q + 5]), tc_pack2(v[8 * q + 6], v[8 * q + 7]));
 }
 
+// support_to_scalar(softmax(logits)) (muax/model.py:273-274 + muax/utils.py:94-102) of one accumulator row of NP
+// (padded) columns held in registers: max, exponentials, sum and expectation without a branch or a second TMEM read.
+template <int NP>
+__device__ __forceinline__ float tc_head_scalar(uint32_t trow, const float* bias, int n, int S) {
+  float v[NP];
+#pragma unroll
+  for (int c0 = 0; c0 < NP; c0 += 16) {
+    float w[16];
+    tc_ld16(trow + (uint32_t)c0, w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[c0 + i] = w[i];
+  }
+  tc_add_bias<NP>(v, bias, 0);
+  float mx = -mz_inf();
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    v[i] = i < n ? v[i] : -mz_inf();
+    mx = fmaxf(mx, v[i]);
+  }
+  float sum = 0.0f, x = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const float e = tc_ex2((v[i] - mx) * kTcLog2e);  // padded columns: 2^-inf = 0
+    sum += e;
+    x += (float)(i - S) * e;
+  }
+  return mz_inv_scaling(x / sum);
+}
+
+#ifdef MZ_TC_CLOCKS
+// timeline of CTA 0 (cycles since kernel start): [0] prologue done, [1] A operand written; per step s:
+// [4s+2] MMA issuer past bar_aready, [4s+3] last MMA of the step issued, [4s+4] epilogue past bar_acc, [4s+5] epilogue done
+#define MZ_TCCLK(i) do { if (blockIdx.x == 0) tc_clk[(i)] = clock64() - tc_t0; } while (0)
+#else
+#define MZ_TCCLK(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
-  __shared__ __align__(8) uint64_t bar_full[kTcStages], bar_empty[kTcStages], bar_acc, bar_aready;
+#ifdef MZ_TC_CLOCKS
+  __shared__ long long tc_clk[4 * kTcMaxSteps + 8];
+  const long long tc_t0 = clock64();
+#endif
+  __shared__ __align__(8) uint64_t bar_full[kTcMaxStages], bar_empty[kTcMaxStages], bar_acc, bar_aready;
   __shared__ uint32_t tmem_base_sh;
   __shared__ float row_lo[2][kTcM], row_hi[2][kTcM];  // partial row min / max of the two column halves
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  asm volatile("griddepcontrol.launch_dependents;");  // the next kernel of the stream may begin its own prologue
   // dynamic shared memory: A operand (input | one-hot, later the next state) | hidden 0 | hidden 1 | weight ring | biases
   uint8_t* stages = tc_smem + a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes;
-  float* bias_all = reinterpret_cast<float*>(stages + (size_t)kTcStages * a.stage_bytes);
+  float* bias_all = reinterpret_cast<float*>(stages + (size_t)a.n_stages * a.stage_bytes);
+  const uint32_t n_stages = (uint32_t)a.n_stages;
   const uint32_t smem_sh = smem_u32(tc_smem);
   auto buf_sh = [&](int which) -> uint32_t {
     return smem_sh + (which == kBufA ? 0u : (uint32_t)a.bufA_bytes + (which == kBufH0 ? 0u : (uint32_t)a.bufH_bytes));
@@ -199,7 +276,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
   const uint32_t stages_sh = smem_u32(stages);
 
   if (tid == 0) {
-    for (int i = 0; i < kTcStages; ++i) {
+    for (int i = 0; i < a.n_stages; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
@@ -212,29 +289,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // every layer's bias, zero padded to npad, once per CTA: the epilogues read it from shared memory (a global load per
-  // element left every epilogue iteration waiting for L2: profiles/r02_recurrent_tc_v1_*)
-  for (int s = 0; s < a.n_steps; ++s) {
-    const float* b = a.raw + a.steps[s].b_off;
-    for (int c = tid; c < a.steps[s].npad; c += kTcThreads) bias_all[a.steps[s].bias_sh + c] = c < a.steps[s].n ? __ldg(b + c) : 0.0f;
-  }
+  // every layer's bias, zero padded to npad, once per CTA: the epilogues read it from shared memory.  One flat copy of
+  // the packed table: all of a thread's loads are in flight together (a loop per layer paid one L2 round trip per layer)
+  for (int i = tid; i < a.bias_floats; i += kTcThreads) bias_all[i] = __ldg(a.bias_table + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
   const int row0 = blockIdx.x * kTcM;
+  if (tid == 0) MZ_TCCLK(0);
 
   if (warp == kTcEpiWarps + 1) {
     // ---- TMA producer: streams every layer's operand image, chunk by chunk, through the ring
     if (lane == 0) {
       uint32_t g = 0;
       for (int s = 0; s < a.n_steps; ++s) {
-        const int kpad = a.steps[s].k16 * 16, npad = a.steps[s].npad;
+        const int kpad = a.steps[s].k16 * 16, npad = a.steps[s].npad, kc = a.steps[s].kc;
         const __nv_bfloat16* img = a.images + a.steps[s].img_off;
-        for (int k0 = 0; k0 < kpad; k0 += kTcKC, ++g) {
-          const uint32_t st = g % kTcStages, round = g / kTcStages;
+        for (int k0 = 0; k0 < kpad; k0 += kc, ++g) {
+          const uint32_t st = g % n_stages, round = g / n_stages;
           tc_mbar_wait(&bar_empty[st], (round & 1u) ^ 1u);  // the MMAs that read the stage's last chunk are complete
-          const uint32_t bytes = (uint32_t)(npad * min(kTcKC, kpad - k0)) * 2u;
+          const uint32_t bytes = (uint32_t)(npad * min(kc, kpad - k0)) * 2u;
           mbar_expect_tx(&bar_full[st], bytes);
           tma_bulk_g2s(stages + (size_t)st * a.stage_bytes, img + (size_t)k0 * npad, bytes, &bar_full[st]);
         }
@@ -246,17 +321,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
     if (lane == 0) {
       uint32_t g = 0;
       for (int s = 0; s < a.n_steps; ++s) {
-        const int kpad = a.steps[s].k16 * 16, npad = a.steps[s].npad;
+        const int kpad = a.steps[s].k16 * 16, npad = a.steps[s].npad, kc0 = a.steps[s].kc;
         const uint32_t idesc = tc_idesc(npad);
         const uint32_t a_sh = buf_sh(a.steps[s].a_buf);
         tc_mbar_wait(&bar_aready, (uint32_t)(s & 1));  // the A operand is in shared memory, the accumulators are drained
         tc_fence_after();
-        for (int k0 = 0; k0 < kpad; k0 += kTcKC, ++g) {
-          const uint32_t st = g % kTcStages, round = g / kTcStages;
+        MZ_TCCLK(4 * s + 2);
+        for (int k0 = 0; k0 < kpad; k0 += kc0, ++g) {
+          const uint32_t st = g % n_stages, round = g / n_stages;
           tc_mbar_wait(&bar_full[st], round & 1u);
           tc_fence_after();
           const uint32_t b_sh = stages_sh + st * (uint32_t)a.stage_bytes;
-          const int kc = min(kTcKC, kpad - k0);
+          const int kc = min(kc0, kpad - k0);
           for (int j = 0; j < kc; j += 16) {
             // one MMA consumes two 16-byte k-chunks of every row of A and of every row of W^T
             const uint64_t adesc = tc_smem_desc(a_sh + (uint32_t)((k0 + j) / 8) * kTcChunkPitch, kTcChunkPitch, 128u);
@@ -266,6 +342,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
           tc_commit(&bar_empty[st]);  // frees the stage when these MMAs have read it
         }
         tc_commit(&bar_acc);  // the layer's accumulators are complete
+        MZ_TCCLK(4 * s + 3);
       }
     }
     __syncwarp();
@@ -278,15 +355,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
     const int rb = min(row, a.B - 1);
     const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     {  // [input row, one-hot(action)] -> A operand (muax/nn.py:105-108); the two halves take alternate 16-byte chunks
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: everything above overlapped
+                                                           // the kernel that selected (parent, action)
       const int parent = a.parent != nullptr ? a.parent[rb] : 0;
       const int action = a.action != nullptr ? a.action[rb] : -1;
       const int D = a.in_dim;
-      const float* src = a.in + (size_t)rb * a.in_row_stride + (size_t)parent * D;
+      const float* src = a.in + (size_t)rb * a.in_row_stride + (size_t)parent * D;  // surplus rows shadow the last row
       const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
       const int kpad = a.kx16 * 16;
-      for (int k0 = 8 * half; k0 < kpad; k0 += 16) {
+      const uint32_t dst_sh = buf_sh(kBufA) + (uint32_t)r * 16u;
+      int k0 = 8 * half;
+      // eight chunks per round: sixteen independent 128-bit loads in flight before the first store (one chunk at a
+      // time paid one L2 round trip per chunk: 7 us of a 256-wide row)
+      for (; vec && k0 + 16 * 7 + 8 <= D; k0 += 16 * 8) {
+        float4 lo4[8], hi4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          lo4[j] = __ldcs(reinterpret_cast<const float4*>(src + k0 + 16 * j));
+          hi4[j] = __ldcs(reinterpret_cast<const float4*>(src + k0 + 16 * j + 4));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          tc_sts16(dst_sh + (uint32_t)((k0 + 16 * j) / 8) * kTcChunkPitch, tc_pack2(lo4[j].x, lo4[j].y),
+                   tc_pack2(lo4[j].z, lo4[j].w), tc_pack2(hi4[j].x, hi4[j].y), tc_pack2(hi4[j].z, hi4[j].w));
+      }
+      for (; k0 < kpad; k0 += 16) {
         float v[8];
-        if (vec && live && k0 + 8 <= D) {
+        if (vec && k0 + 8 <= D) {
           const float4 lo4 = __ldcs(reinterpret_cast<const float4*>(src + k0));
           const float4 hi4 = __ldcs(reinterpret_cast<const float4*>(src + k0 + 4));
           v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w; v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
@@ -294,14 +389,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int k = k0 + i;
-            v[i] = (live && k < D) ? __ldcs(src + k) : ((live && action >= 0 && k == D + action) ? 1.0f : 0.0f);
+            v[i] = k < D ? __ldcs(src + k) : ((action >= 0 && k == D + action) ? 1.0f : 0.0f);
           }
         }
-        tc_sts16(buf_sh(kBufA) + (uint32_t)(k0 / 8) * kTcChunkPitch + (uint32_t)r * 16u, tc_pack2(v[0], v[1]),
-                 tc_pack2(v[2], v[3]), tc_pack2(v[4], v[5]), tc_pack2(v[6], v[7]));
+        tc_sts16(dst_sh + (uint32_t)(k0 / 8) * kTcChunkPitch, tc_pack2(v[0], v[1]), tc_pack2(v[2], v[3]),
+                 tc_pack2(v[4], v[5]), tc_pack2(v[6], v[7]));
       }
       tc_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) reads
       tc_mbar_arrive(&bar_aready);
+      if (tid == 0) MZ_TCCLK(1);
     }
     for (int s = 0; s < a.n_steps; ++s) {
       const TcStep& st = a.steps[s];
@@ -312,11 +408,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
       const int cb = half == 0 ? 0 : split, ce = half == 0 ? split : npad;
       tc_mbar_wait(&bar_acc, (uint32_t)(s & 1));
       tc_fence_after();
+      if (tid == 0) MZ_TCCLK(4 * s + 4);
       if (st.epi == kEpiHidden) {
         const uint32_t out_sh = buf_sh(st.out_buf) + (uint32_t)r * 16u;
         int c0 = cb;
-        for (; c0 + 32 <= ce; c0 += 32) tc_epi_hidden<32>(trow, c0, n, bias, a.act_kind, out_sh);
-        for (; c0 < ce; c0 += 16) tc_epi_hidden<16>(trow, c0, n, bias, a.act_kind, out_sh);
+        for (; c0 + 32 <= ce; c0 += 32) tc_epi_hidden<32>(trow, c0, bias, a.act_kind, out_sh);
+        for (; c0 < ce; c0 += 16) tc_epi_hidden<16>(trow, c0, bias, a.act_kind, out_sh);
       } else if (st.epi == kEpiNextState) {
         // min_max_normalize (muax/nn.py:37-44) over the row, then the new embedding: fp32 to global (expand stores it
         // into the tree), bf16 into Prediction's A operand.  The two column halves of a row meet through shared memory.
@@ -325,13 +422,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
           for (int c0 = cb; c0 < ce; c0 += 16) {
             float v[16];
             tc_ld16(trow + (uint32_t)c0, v);
+            tc_add_bias<16>(v, bias, c0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < n) {
-                const float y = v[i] + bias[c0 + i];
-                lo = fminf(lo, y);
-                hi = fmaxf(hi, y);
-              }
+            for (int i = 0; i < 16; ++i) {
+              const bool in = c0 + i < n;
+              lo = fminf(lo, in ? v[i] : mz_inf());
+              hi = fmaxf(hi, in ? v[i] : -mz_inf());
+            }
           }
           row_lo[half][r] = lo;
           row_hi[half][r] = hi;
@@ -341,23 +438,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
         }
         float scale = hi - lo;
         if (scale < 1e-5f) scale += 1e-5f;
-        const float inv = 1.0f / scale;
+        const float inv = st.minmax ? 1.0f / scale : 1.0f;
+        const float sub = st.minmax ? lo : 0.0f;
         const uint32_t out_sh = buf_sh(st.out_buf) + (uint32_t)r * 16u;
         float* dst = a.next_emb + (size_t)rb * a.out_dim;
         const bool dst_vec = (a.out_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(a.next_emb) & 15) == 0;
         for (int c0 = cb; c0 < ce; c0 += 16) {
           float v[16];
           tc_ld16(trow + (uint32_t)c0, v);
+          tc_add_bias<16>(v, bias, c0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = c0 + i;
-            float y = 0.0f;
-            if (c < n) {
-              y = v[i] + bias[c];
-              if (st.minmax) y = (y - lo) * inv;
-            }
-            v[i] = y;
-          }
+          for (int i = 0; i < 16; ++i) v[i] = c0 + i < n ? (v[i] - sub) * inv : 0.0f;
           if (live) {
             if (dst_vec && c0 + 16 <= n) {
 #pragma unroll
@@ -378,79 +469,96 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
         for (int c0 = cb; c0 < ce; c0 += 16) {
           float v[16];
           tc_ld16(trow + (uint32_t)c0, v);
+          tc_add_bias<16>(v, bias, c0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = c0 + i;
-            if (live && c < n) a.logits[(size_t)row * a.A + c] = v[i] + bias[c];
-          }
+          for (int i = 0; i < 16; ++i)
+            if (live && c0 + i < n) a.logits[(size_t)row * a.A + c0 + i] = v[i];
         }
       } else if (half == 0) {
-        // support_to_scalar(softmax(logits)) (muax/model.py:273-274 + muax/utils.py:94-102): max, sum of exps,
-        // expectation — a narrow row (2S + 1 logits), finished by one thread
-        float mx = -mz_inf();
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-          float v[16];
-          tc_ld16(trow + (uint32_t)c0, v);
+        // support_to_scalar(softmax(logits)): a narrow row (2S + 1 logits), finished by one thread in registers
+        float y;
+        if (npad <= 16) y = tc_head_scalar<16>(trow, bias, n, a.S);
+        else if (npad <= 32) y = tc_head_scalar<32>(trow, bias, n, a.S);
+        else if (npad <= 48) y = tc_head_scalar<48>(trow, bias, n, a.S);
+        else if (npad <= 64) y = tc_head_scalar<64>(trow, bias, n, a.S);
+        else {  // wide supports: three passes over tensor memory
+          float mx = -mz_inf();
+          for (int c0 = 0; c0 < npad; c0 += 16) {
+            float v[16];
+            tc_ld16(trow + (uint32_t)c0, v);
+            tc_add_bias<16>(v, bias, c0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < n) mx = fmaxf(mx, v[i] + bias[c0 + i]);
-        }
-        float sum = 0.0f;
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-          float v[16];
-          tc_ld16(trow + (uint32_t)c0, v);
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, c0 + i < n ? v[i] : -mz_inf());
+          }
+          float sum = 0.0f, x = 0.0f;
+          for (int c0 = 0; c0 < npad; c0 += 16) {
+            float v[16];
+            tc_ld16(trow + (uint32_t)c0, v);
+            tc_add_bias<16>(v, bias, c0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < n) sum += __expf(v[i] + bias[c0 + i] - mx);
+            for (int i = 0; i < 16; ++i) {
+              const float e = c0 + i < n ? tc_ex2((v[i] - mx) * kTcLog2e) : 0.0f;
+              sum += e;
+              x += (float)(c0 + i - a.S) * e;
+            }
+          }
+          y = mz_inv_scaling(x / sum);
         }
-        const float inv = 1.0f / sum;
-        float x = 0.0f;
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-          float v[16];
-          tc_ld16(trow + (uint32_t)c0, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < n) x += (float)(c0 + i - a.S) * (__expf(v[i] + bias[c0 + i] - mx) * inv);
-        }
-        const float y = mz_inv_scaling(x);
         if (live) (st.epi == kEpiReward ? a.reward : a.value)[row] = y;
       }
       tc_fence_before();       // this thread's TMEM loads are complete (tcgen05.wait::ld) and ordered before ...
       tc_fence_proxy_async();  // ... and its shared-memory stores visible to ... the next step's MMAs
       tc_mbar_arrive(&bar_aready);
+      if (tid == 0) MZ_TCCLK(4 * s + 5);
     }
   }
   tc_fence_before();
   __syncthreads();
+#ifdef MZ_TC_CLOCKS
+  if (blockIdx.x == 0 && tid == 0) {
+    printf("tc clk | prologue %lld A %lld |", tc_clk[0], tc_clk[1]);
+    for (int s = 0; s < a.n_steps; ++s)
+      printf(" s%d[k16=%d n=%d] mma_go %lld mma_issued %lld acc %lld epi_done %lld |", s, a.steps[s].k16, a.steps[s].npad,
+             tc_clk[4 * s + 2], tc_clk[4 * s + 3], tc_clk[4 * s + 4], tc_clk[4 * s + 5]);
+    printf(" end %lld\n", clock64() - tc_t0);
+  }
+#endif
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
   }
 }
 
-// W [K][N] fp32 row-major -> the bf16 operand image of the layer: chunks of kTcKC k-values, inside a chunk
+// W [K][N] fp32 row-major -> the bf16 operand image of the layer: chunks of kc k-values, inside a chunk
 // [k / 8][npad rows][8 k-values], zero padded to kpad x npad.
 __global__ void recurrent_tc_pack_kernel(const float* __restrict__ raw, __nv_bfloat16* __restrict__ img, int64_t w_off,
-                                         int K, int N, int kpad, int npad) {
+                                         int K, int N, int kpad, int npad, int kc) {
   const int total = kpad * npad;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int k = idx / npad, n = idx - k * npad;
     const float v = (k < K && n < N) ? raw[w_off + (int64_t)k * N + n] : 0.0f;
-    const int c = k / kTcKC, kk = k - c * kTcKC;
-    const size_t off = (size_t)c * npad * kTcKC + ((size_t)(kk / 8) * npad + n) * 8 + (kk & 7);
+    const int c = k / kc, kk = k - c * kc;
+    const size_t off = (size_t)c * npad * kc + ((size_t)(kk / 8) * npad + n) * 8 + (kk & 7);
     img[off] = __float2bfloat16_rn(v);
   }
+}
+
+// The bias rows of every step of every program, zero padded to npad, in one table.
+__global__ void recurrent_tc_bias_kernel(const float* __restrict__ raw, float* __restrict__ table, int64_t b_off, int N,
+                                         int npad, int dst) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < npad; c += gridDim.x * blockDim.x)
+    table[dst + c] = c < N ? raw[b_off + c] : 0.0f;
 }
 
 // ------------------------------------------------------------------------------------------ host side
 
 struct TcLayer {
-  int64_t w_off, img_off;
-  int K, N, kpad, npad;
+  int64_t w_off, img_off, b_off;
+  int K, N, kpad, npad, kc, bias_dst;  // bias_dst: float offset of the layer's padded bias row in the bias table
 };
 struct TcProgram {
   TcArgs args{};
-  size_t smem = 0;
+  size_t smem = 0, bias_base = 0;  // bias_base: float offset of the program's rows in the bias table
   bool ok = false;
 };
 struct TcImpl {
@@ -459,7 +567,8 @@ struct TcImpl {
   TcProgram root_emb;  // root from a caller-made embedding: value head, policy head
   std::vector<TcLayer> layers;
   __nv_bfloat16* images = nullptr;
-  size_t image_elems = 0;
+  float* bias_table = nullptr;
+  size_t image_elems = 0, bias_elems = 0;
 };
 
 struct TcHead {
@@ -470,8 +579,16 @@ struct TcHead {
 // One program = a chain of heads over a shared input operand.  Every head's first layer reads buffer A; the head
 // that ends in kEpiNextState overwrites buffer A with its (normalised) output, which the heads after it read.
 static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& heads, int in_dim, bool onehot_actions,
-                     int num_actions, size_t* img, int max_smem, std::string* why) {
+                     int num_actions, size_t* img, size_t* bias_base, int max_smem, std::string* why) {
   TcArgs& a = prog.args;
+  prog.bias_base = *bias_base;
+  const size_t layers0 = impl->layers.size(), img0 = *img;
+  auto fail = [&](const char* msg) {  // a program that cannot be built leaves no layers behind
+    impl->layers.resize(layers0);
+    *img = img0;
+    *why = msg;
+    return false;
+  };
   int max_npad = 16, max_hidden_pad = 16, deepest = 1, n_steps = 0, bias_floats = 0;
   int bufA_k = round_up(in_dim + (onehot_actions ? num_actions : 0), 16);
   for (const TcHead& h : heads) {
@@ -480,13 +597,14 @@ static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& h
     for (int l = 0; l < s.n_layers; ++l) {
       const int K = l == 0 ? h.in : s.in_dim[l], N = s.out_dim[l];
       const int kpad = round_up(K, 16), npad = round_up(N, 16);
-      if (npad > 256) { *why = "a layer is wider than 256 units"; return false; }
-      if (n_steps >= kTcMaxSteps) { *why = "too many layers"; return false; }
+      if (npad > 256) return fail("a layer is wider than 256 units");
+      if (n_steps >= kTcMaxSteps) return fail("too many layers");
       const bool last = l == s.n_layers - 1;
       TcStep& t = a.steps[n_steps++];
       t.a_buf = l == 0 ? kBufA : ((l - 1) & 1 ? kBufH1 : kBufH0);
       t.out_buf = last ? kBufA : (l & 1 ? kBufH1 : kBufH0);
       t.k16 = kpad / 16;
+      t.kc = std::min(kpad, std::max(16, kTcStageBytes / (npad * 2) / 16 * 16));
       t.n = N;
       t.npad = npad;
       t.epi = last ? h.final_epi : kEpiHidden;
@@ -495,7 +613,8 @@ static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& h
       bias_floats += npad;
       t.b_off = s.b_off[l];
       t.img_off = (int64_t)*img;
-      impl->layers.push_back(TcLayer{s.w_off[l], (int64_t)*img, K, N, kpad, npad});
+      impl->layers.push_back(TcLayer{s.w_off[l], (int64_t)*img, s.b_off[l], K, N, kpad, npad, t.kc,
+                                     (int)(*bias_base + t.bias_sh)});
       *img += (size_t)kpad * npad;
       max_npad = std::max(max_npad, npad);
       if (!last) max_hidden_pad = std::max(max_hidden_pad, npad);
@@ -508,14 +627,17 @@ static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& h
   a.bufA_bytes = bufA_k / 8 * (int)kTcChunkPitch;
   a.bufH_bytes = max_hidden_pad / 8 * (int)kTcChunkPitch;
   a.bufH1_bytes = deepest >= 3 ? a.bufH_bytes : 0;
-  a.stage_bytes = max_npad * kTcKC * 2;
+  a.stage_bytes = kTcStageBytes;
   a.bias_floats = bias_floats;
   int cols = 32;
   while (cols < max_npad) cols <<= 1;
   a.tmem_cols = cols;
-  prog.smem = (size_t)a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes + (size_t)kTcStages * a.stage_bytes +
-              (size_t)bias_floats * 4 + 128;
-  if (prog.smem > (size_t)max_smem - 2048) { *why = "operands do not fit shared memory"; return false; }
+  const size_t fixed = (size_t)a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes + (size_t)bias_floats * 4 + 128;
+  const size_t budget = (size_t)max_smem - 2048;
+  if (fixed + 2 * (size_t)kTcStageBytes > budget) return fail("operands do not fit shared memory");
+  a.n_stages = (int)std::min<size_t>(kTcMaxStages, (budget - fixed) / kTcStageBytes);
+  prog.smem = fixed + (size_t)a.n_stages * kTcStageBytes;
+  *bias_base += bias_floats;
   prog.ok = true;
   return true;
 }
@@ -536,22 +658,22 @@ int recurrent_tc_init(RecurrentTcState& st, const Net& net, int batch, int devic
   TcImpl* impl = new TcImpl();
   const int E = net.embed_dim, A = net.num_actions, F = 2 * net.support_size + 1;
   const int max_smem = (int)prop.sharedMemPerBlockOptin;
-  size_t img = 0;
+  size_t img = 0, bias_base = 0;
   bool ok = F == net.dyn_r.out_dim[net.dyn_r.n_layers - 1];
   if (!ok) st.why = "support size mismatch";
   // heads in execution order; the reward head runs before the next-state head overwrites their shared input
   if (ok)
     ok = tc_build(impl, impl->rec, {{&net.dyn_r, E + A, kEpiReward, 0}, {&net.dyn_ns, E + A, kEpiNextState, net.dyn_minmax},
                                     {&net.pred_v, E, kEpiValue, 0}, {&net.pred_pi, E, kEpiPolicy, 0}},
-                  E, true, A, &img, max_smem, &st.why);
+                  E, true, A, &img, &bias_base, max_smem, &st.why);
   if (ok) {
     std::string why;  // the root programs are optional: without them the root runs on the fp32 kernels
     tc_build(impl, impl->root_emb, {{&net.pred_v, E, kEpiValue, 0}, {&net.pred_pi, E, kEpiPolicy, 0}}, E, false, A, &img,
-             max_smem, &why);
+             &bias_base, max_smem, &why);
     if (net.obs_dim > 0 && net.repr.n_layers > 0)
       tc_build(impl, impl->root_obs, {{&net.repr, net.obs_dim, kEpiNextState, net.repr_minmax}, {&net.pred_v, E, kEpiValue, 0},
                                       {&net.pred_pi, E, kEpiPolicy, 0}},
-               net.obs_dim, false, A, &img, max_smem, &why);
+               net.obs_dim, false, A, &img, &bias_base, max_smem, &why);
   }
   size_t smem_max = 0;
   for (TcProgram* p : {&impl->rec, &impl->root_obs, &impl->root_emb})
@@ -561,7 +683,9 @@ int recurrent_tc_init(RecurrentTcState& st, const Net& net, int batch, int devic
     ok = false;
     st.why = "cudaFuncSetAttribute failed";
   }
-  if (ok && cudaMalloc((void**)&impl->images, img * sizeof(__nv_bfloat16) + 16) != cudaSuccess) {
+  if (ok && (cudaMalloc((void**)&impl->images, img * sizeof(__nv_bfloat16) + 16) != cudaSuccess ||
+             cudaMalloc((void**)&impl->bias_table, (bias_base + 4) * sizeof(float)) != cudaSuccess)) {
+    if (impl->images) cudaFree(impl->images);
     cudaGetLastError();
     delete impl;
     *err = "recurrent_tc: cudaMalloc(operand images) failed";
@@ -572,9 +696,11 @@ int recurrent_tc_init(RecurrentTcState& st, const Net& net, int batch, int devic
     return 0;
   }
   impl->image_elems = img;
+  impl->bias_elems = bias_base;
   for (TcProgram* p : {&impl->rec, &impl->root_obs, &impl->root_emb}) {
     TcArgs& a = p->args;
     a.images = impl->images;
+    a.bias_table = impl->bias_table + p->bias_base;
     a.A = A;
     a.S = net.support_size;
     a.act_kind = net.activation;
@@ -589,6 +715,7 @@ void recurrent_tc_destroy(RecurrentTcState& st) {
   TcImpl* impl = static_cast<TcImpl*>(st.impl);
   if (impl != nullptr) {
     if (impl->images) cudaFree(impl->images);
+    if (impl->bias_table) cudaFree(impl->bias_table);
     delete impl;
   }
   st.impl = nullptr;
@@ -603,18 +730,30 @@ int recurrent_tc_pack(RecurrentTcState& st, const Net& net, const float* raw_wei
   for (const TcLayer& L : impl->layers) {
     const int total = L.kpad * L.npad;
     recurrent_tc_pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(raw_weights_dev, impl->images + L.img_off, L.w_off,
-                                                                      L.K, L.N, L.kpad, L.npad);
-    *launches += 1;
+                                                                      L.K, L.N, L.kpad, L.npad, L.kc);
+    recurrent_tc_bias_kernel<<<1, 256, 0, stream>>>(raw_weights_dev, impl->bias_table, L.b_off, L.N, L.npad, L.bias_dst);
+    *launches += 2;
   }
-  for (TcProgram* p : {&impl->rec, &impl->root_obs, &impl->root_emb}) p->args.raw = raw_weights_dev;
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 static int tc_run(const TcProgram& prog, TcArgs a, int B, cudaStream_t stream, int64_t* launches, std::string* err) {
   a.B = B;
   void* args[] = {&a};
-  const int grid = (B + kTcM - 1) / kTcM;
-  const cudaError_t e = cudaLaunchKernel((void*)recurrent_tc_kernel, dim3(grid), dim3(kTcThreads), args, prog.smem, stream);
+  // programmatic dependent launch: the kernel may start while the kernel before it in the stream is still running —
+  // barrier setup, TMEM allocation, the bias table and the first weight stages do not depend on it — and executes
+  // griddepcontrol.wait before it reads (parent, action) and the embeddings
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((B + kTcM - 1) / kTcM);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = prog.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)recurrent_tc_kernel, args);
   *launches += 1;
   if (e != cudaSuccess) {
     *err = std::string("recurrent_tc launch failed: ") + cudaGetErrorString(e);

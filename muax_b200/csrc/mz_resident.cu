@@ -472,26 +472,31 @@ namespace mz {
 
 // ------------------------------------------------------------------------------------------ tie-break noise pre-pass
 
-// One thread per (tree, simulation): per-tree key = split(sim_key, B_global)[global row]; then per level
-// (key, sel) = split(key); noise[a] = 1e-7 * uniform(sel, (A,))[a]  (Appendix A.3, A.5, A.7).  Row = K levels x A.
-__global__ void __launch_bounds__(128) resident_noise_kernel(SearchParams p, int B, int A, int K,
+// One thread per (tree, simulation) of the simulations [sim0, sim1): per-tree key = split(sim_key, B_global)[global
+// row]; then per level (key, sel) = split(key); noise[a] = 1e-7 * uniform(sel, (A,))[a]  (Appendix A.3, A.5, A.7).
+// Row = K levels x A.  Simulation-major (a warp works on one simulation of 32 trees), so the level bound is
+// warp-uniform: simulation s walks a tree of s + 1 nodes, its path has at most s + 1 levels (and then never reaches the
+// continuation key, which is only read at depth K).
+__global__ void __launch_bounds__(128) resident_noise_kernel(SearchParams p, int B, int A, int K, int sim0, int sim1,
                                                              float* __restrict__ table, uint32_t* __restrict__ cont) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int NS = p.num_simulations;
-  if (idx >= B * NS) return;
-  const int b = idx / NS, sim = idx - b * NS;
+  if (idx >= B * (sim1 - sim0)) return;
+  const int sim = sim0 + idx / B, b = idx % B;
+  const size_t pair = (size_t)b * NS + sim;
   uint32_t k0, k1;
   split_key(p.sim_keys[2 * sim], p.sim_keys[2 * sim + 1], (uint32_t)p.global_batch, (uint32_t)(p.batch_offset + b),
             p.prng_mode, k0, k1);
-  float* row = table + (size_t)idx * K * A;
-  for (int d = 0; d < K; ++d) {
+  float* row = table + pair * K * A;
+  const int levels = min(K, sim + 1);
+  for (int d = 0; d < levels; ++d) {
     uint32_t s0, s1;
     split_key(k0, k1, 2u, 1u, p.prng_mode, s0, s1);
     split_key(k0, k1, 2u, 0u, p.prng_mode, k0, k1);
     for (int x = 0; x < A; ++x) row[d * A + x] = tie_break_noise(bits_word(s0, s1, (uint32_t)A, (uint32_t)x, p.prng_mode));
   }
-  cont[2 * (size_t)idx] = k0;
-  cont[2 * (size_t)idx + 1] = k1;
+  cont[2 * pair] = k0;
+  cont[2 * pair + 1] = k1;
 }
 
 // Records -> the mctx SoA arrays of the handle (mz_get_tree view).  One thread per (tree, node); nodes that were
@@ -1097,9 +1102,10 @@ int records_reserve(ResidentState& st, int B, int NS, int A, int PL, std::string
 
 // Tie-break noise ahead of the search (MuZero policy only: the Gumbel selectors ignore their key): fills
 // st.noise_table [B][NS][K][A] and st.cont_keys for the first K = min(levels, PL, 1 GiB cap) levels.  *K_out = 0 when
-// no table is produced.
-int records_noise_prepass(ResidentState& st, const SearchParams& p, int B, int A, int levels, int PL,
-                          cudaStream_t stream, int64_t* launches, int* K_out, std::string* err) {
+// no table is produced.  reserve + range: the same in two steps, for callers that produce the table in simulation
+// ranges on a side stream (the throughput mode, mz_treewarp.cu).
+int records_noise_reserve(ResidentState& st, const SearchParams& p, int B, int A, int levels, int PL, int* K_out,
+                          std::string* err) {
   *K_out = 0;
   const int NS = p.num_simulations;
   if (p.policy != MZ_POLICY_MUZERO || NS <= 0 || levels <= 0) return 0;
@@ -1131,9 +1137,23 @@ int records_noise_prepass(ResidentState& st, const SearchParams& p, int B, int A
     }
     st.cont_capacity = pairs;
   }
-  resident_noise_kernel<<<(unsigned)((pairs + 127) / 128), 128, 0, stream>>>(p, B, A, K, st.noise_table, st.cont_keys);
-  *launches += 1;
   *K_out = K;
+  return 0;
+}
+
+void records_noise_range(ResidentState& st, const SearchParams& p, int B, int A, int K, int sim0, int sim1,
+                         cudaStream_t stream, int64_t* launches) {
+  if (sim1 <= sim0 || K <= 0) return;
+  const size_t pairs = (size_t)B * (sim1 - sim0);
+  resident_noise_kernel<<<(unsigned)((pairs + 127) / 128), 128, 0, stream>>>(p, B, A, K, sim0, sim1, st.noise_table,
+                                                                            st.cont_keys);
+  *launches += 1;
+}
+
+int records_noise_prepass(ResidentState& st, const SearchParams& p, int B, int A, int levels, int PL,
+                          cudaStream_t stream, int64_t* launches, int* K_out, std::string* err) {
+  if (records_noise_reserve(st, p, B, A, levels, PL, K_out, err)) return 1;
+  records_noise_range(st, p, B, A, *K_out, 0, p.num_simulations, stream, launches);
   return 0;
 }
 

@@ -55,6 +55,10 @@ int net_weight_bytes(const Net& net);  // bytes of the raw fp32 blob the stacks 
 int records_reserve(ResidentState& st, int B, int NS, int A, int PL, std::string* err);
 int records_noise_prepass(ResidentState& st, const SearchParams& p, int B, int A, int levels, int PL,
                           cudaStream_t stream, int64_t* launches, int* K_out, std::string* err);
+int records_noise_reserve(ResidentState& st, const SearchParams& p, int B, int A, int levels, int PL, int* K_out,
+                          std::string* err);
+void records_noise_range(ResidentState& st, const SearchParams& p, int B, int A, int K, int sim0, int sim1,
+                         cudaStream_t stream, int64_t* launches);
 
 // Records of the last search -> the handle's SoA arrays (no-op unless a resident search ran since the last call).
 int resident_unpack(ResidentState& st, const Tree& tree, float gamma, std::string* err);
