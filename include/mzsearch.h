@@ -114,6 +114,12 @@ typedef struct mz_search_args {
   uint32_t key0, key1;    /* the jax PRNGKey words */
   uint32_t flags;         /* MZ_FLAG_* */
   int32_t precision;      /* MZ_PRECISION_* */
+  /* mctx.stochastic_muzero_policy (muax/policy.py:50-67), callback mode only (mz_begin .. mz_finish): the handle's
+   * num_actions is A' = A + C (decision actions then chance outcomes); num_decision_actions = A (> 0 switches the
+   * mode on).  Nodes at even depth are decision nodes (pUCT over A' with -inf priors on the chance slots), nodes at
+   * odd depth are afterstates (argmax prior / (visits + 1)); root noise, invalid-action mask, visit summary and the
+   * final draw see the A decision actions only.  The caller's recurrent_fn plays mctx's stochastic_recurrent_fn. */
+  int32_t num_decision_actions;
 } mz_search_args;
 
 /* Device views of the search tree after a search (mctx.Tree field names).

@@ -44,7 +44,8 @@ class SearchArgs(ctypes.Structure):
         "engine")] + [(n, ctypes.c_float) for n in (
             "temperature", "dirichlet_fraction", "dirichlet_alpha", "pb_c_init", "pb_c_base", "gumbel_scale",
             "value_scale", "maxvisit_init")] + [("key0", ctypes.c_uint32), ("key1", ctypes.c_uint32),
-                                                ("flags", ctypes.c_uint32), ("precision", ctypes.c_int32)])
+                                                ("flags", ctypes.c_uint32), ("precision", ctypes.c_int32),
+                                               ("num_decision_actions", ctypes.c_int32)])
 
 
 class TreeView(ctypes.Structure):

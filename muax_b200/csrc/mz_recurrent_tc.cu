@@ -29,14 +29,19 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace mz {
 
 constexpr int kTcM = 128;        // rows per CTA
-constexpr int kTcStageBytes = 16384;  // one stage of the weight ring: a layer is cut into chunks of as many k values
-                                      // (a multiple of 16) as fit — 32 at N = 256, the whole layer for narrow ones
-constexpr int kTcMaxStages = 8;  // weight ring depth: as many stages (2 .. 8) as shared memory has room for
+constexpr int kTcStageBytes = 16384;  // unit of the weight ring's stage size (16 or 32 KB): a layer is cut into chunks of as
+                                      // many k values (a multiple of 16) as fit a stage — the whole layer for narrow ones
+constexpr int kTcMaxStages = 8;
+static int tc_stage_env() {  // MZ_TC_STAGE_KB: A/B knob; 0 = choose per program (tc_build)
+  static const int v = getenv("MZ_TC_STAGE_KB") != nullptr ? std::max(8, std::min(64, atoi(getenv("MZ_TC_STAGE_KB")))) * 1024 : 0;
+  return v;
+}  // weight ring depth: as many stages (2 .. 8) as shared memory has room for
 constexpr int kTcMaxSteps = 32;  // 4 heads x MZ_MAX_LAYERS
 constexpr int kTcEpiWarps = 8;   // epilogue warps: warp w reads TMEM lanes 32 * (w % 4) .. + 31, column half w / 4
 constexpr int kTcEpiThreads = 32 * kTcEpiWarps;
@@ -49,7 +54,7 @@ enum { kBufA = 0, kBufH0 = 1, kBufH1 = 2 };
 struct TcStep {
   int32_t a_buf, out_buf;  // A operand of the GEMM / buffer the epilogue writes (hidden and next-state steps)
   int32_t k16;             // K / 16 after padding
-  int32_t kc;              // k values per weight chunk (multiple of 16): kc * npad * 2 bytes <= kTcStageBytes
+  int32_t kc;              // k values per weight chunk (multiple of 16): kc * npad * 2 bytes <= stage_bytes
   int32_t n, npad;         // true and padded (multiple of 16) output width
   int32_t epi;
   int32_t bias_sh;         // float offset of the layer's (zero-padded) bias in the shared-memory bias table
@@ -69,10 +74,21 @@ struct TcArgs {
   int32_t in_dim;           // E, or obs_dim in root mode
   const int32_t* parent;    // [B] or null
   const int32_t* action;    // [B] or null: one-hot(action) follows the in_dim input columns (muax/nn.py:105-108)
+  // the throughput mode's tree embeddings, bf16 (the operand precision): node rows of `es` elements (E rounded up to
+  // 8, zero padded), `tree16_stride` elements per tree.  in16: rows are gathered from [b][parent[b]] instead of `in`;
+  // out16: the next state is stored at [b][next[b]] (16-byte pieces, coalesced through the A operand in shared memory)
+  const __nv_bfloat16* in16;
+  __nv_bfloat16* out16;
+  const int32_t* next;
+  int64_t tree16_stride;
+  int32_t es;
   float *reward, *value, *logits, *next_emb;
   int32_t B, A, S, act_kind, out_dim;  // out_dim: width of next_emb rows (E)
   int32_t kx16;             // k16 of the input operand
   int32_t bufA_bytes, bufH_bytes, bufH1_bytes, stage_bytes, n_stages, bias_floats, tmem_cols;  // bufH1_bytes = 0 unless a head has >= 3 layers
+  // hidden activations in tensor memory instead of shared memory (the A operand of the next layer is then read from
+  // TMEM: `tcgen05.mma [d], [a], b-desc`): bf16 pairs packed into 32-bit columns h_col[0] / h_col[1] .. of the allocation
+  int32_t h_tmem, h_col[2];
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -94,6 +110,21 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// One lane of a converged warp (cute::elect_one_sync).  A region guarded by this predicate is known to the compiler to
+// run on a single thread: tcgen05.mma / commit / bulk copies inside it become straight uniform-datapath instructions.
+// Guarded by `lane == 0` instead, every one of them is wrapped in an ELECT / BRA.U.ANY loop — 224 against 68 cycles per
+// N = 32 MMA issued (tools/probes/mma_probe.cu, profiles/r02_mma_probe.txt).
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -122,6 +153,29 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same MMA with the A operand in tensor memory (lane = row, one 32-bit column = two consecutive k values).
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers.
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -217,6 +271,20 @@ __device__ __forceinline__ void tc_epi_hidden(uint32_t trow, int c0, const float
              tc_pack2(v[8 * q + 2], v[8 * q + 3]), tc_pack2(v[8 * q + 4], v[8 * q + 5]), tc_pack2(v[8 * q + 6], v[8 * q + 7]));
 }
 
+// The same, with the bf16 pairs stored into tensor memory (columns h_taddr + c0 / 2 ..).
+template <int W>
+__device__ __forceinline__ void tc_epi_hidden_tmem(uint32_t trow, int c0, const float* bias, int act_kind, uint32_t h_taddr) {
+  float v[W];
+  tc_ldw<W>(trow + (uint32_t)c0, v);
+  tc_add_bias<W>(v, bias, c0);
+  tc_activate<W>(v, act_kind);
+  uint32_t pk[W / 2];
+#pragma unroll
+  for (int i = 0; i < W / 2; ++i) pk[i] = tc_pack2(v[2 * i], v[2 * i + 1]);
+  if constexpr (W == 32) tc_st16(h_taddr + (uint32_t)(c0 / 2), pk);
+  else tc_st8(h_taddr + (uint32_t)(c0 / 2), pk);
+}
+
 // support_to_scalar(softmax(logits)) (muax/model.py:273-274 + muax/utils.py:94-102) of one accumulator row of NP
 // (padded) columns held in registers: max, exponentials, sum and expectation without a branch or a second TMEM read.
 template <int NP>
@@ -262,6 +330,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
 #endif
   __shared__ __align__(8) uint64_t bar_full[kTcMaxStages], bar_empty[kTcMaxStages], bar_acc, bar_aready;
   __shared__ uint32_t tmem_base_sh;
+  // the step table, copied out of the kernel parameters: a dynamically indexed parameter read is a constant-cache
+  // access of several hundred cycles (per field, per step and per weight chunk it cost ~700 cycles per layer on the MMA
+  // issuer's critical path — profiles/r02_recurrent_tc_timeline_v2.txt)
+  __shared__ TcStep steps_sh[kTcMaxSteps];
   __shared__ float row_lo[2][kTcM], row_hi[2][kTcM];  // partial row min / max of the two column halves
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   asm volatile("griddepcontrol.launch_dependents;");  // the next kernel of the stream may begin its own prologue
@@ -292,6 +364,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
   // every layer's bias, zero padded to npad, once per CTA: the epilogues read it from shared memory.  One flat copy of
   // the packed table: all of a thread's loads are in flight together (a loop per layer paid one L2 round trip per layer)
   for (int i = tid; i < a.bias_floats; i += kTcThreads) bias_all[i] = __ldg(a.bias_table + i);
+  {
+    constexpr int kWords = (int)(sizeof(TcStep) / 4);
+    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(a.steps);
+    uint32_t* dstw = reinterpret_cast<uint32_t*>(steps_sh);
+    for (int i = tid; i < a.n_steps * kWords; i += kTcThreads) dstw[i] = srcw[i];
+  }
+  const int n_steps = a.n_steps, h_tmem = a.h_tmem, h_col0 = a.h_col[0], h_col1 = a.h_col[1], stage_bytes = a.stage_bytes;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -301,45 +380,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
 
   if (warp == kTcEpiWarps + 1) {
     // ---- TMA producer: streams every layer's operand image, chunk by chunk, through the ring
-    if (lane == 0) {
+    if (tc_elect_one()) {
       uint32_t g = 0;
-      for (int s = 0; s < a.n_steps; ++s) {
-        const int kpad = a.steps[s].k16 * 16, npad = a.steps[s].npad, kc = a.steps[s].kc;
-        const __nv_bfloat16* img = a.images + a.steps[s].img_off;
-        for (int k0 = 0; k0 < kpad; k0 += kc, ++g) {
-          const uint32_t st = g % n_stages, round = g / n_stages;
+      const __nv_bfloat16* images = a.images;
+      uint32_t st = 0, round = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        const int kpad = steps_sh[s].k16 * 16, npad = steps_sh[s].npad, kc = steps_sh[s].kc;
+        const __nv_bfloat16* img = images + steps_sh[s].img_off;
+        for (int k0 = 0; k0 < kpad; k0 += kc) {
           tc_mbar_wait(&bar_empty[st], (round & 1u) ^ 1u);  // the MMAs that read the stage's last chunk are complete
           const uint32_t bytes = (uint32_t)(npad * min(kc, kpad - k0)) * 2u;
           mbar_expect_tx(&bar_full[st], bytes);
-          tma_bulk_g2s(stages + (size_t)st * a.stage_bytes, img + (size_t)k0 * npad, bytes, &bar_full[st]);
+          tma_bulk_g2s(stages + (size_t)st * stage_bytes, img + (size_t)k0 * npad, bytes, &bar_full[st]);
+          if (++st == n_stages) { st = 0; ++round; }
         }
       }
     }
     __syncwarp();
   } else if (warp == kTcEpiWarps) {
     // ---- MMA issuer: one thread drives the tensor core
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int s = 0; s < a.n_steps; ++s) {
-        const int kpad = a.steps[s].k16 * 16, npad = a.steps[s].npad, kc0 = a.steps[s].kc;
+    if (tc_elect_one()) {
+      uint32_t st = 0, round = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        const int kpad = steps_sh[s].k16 * 16, npad = steps_sh[s].npad, kc0 = steps_sh[s].kc, a_buf = steps_sh[s].a_buf;
         const uint32_t idesc = tc_idesc(npad);
-        const uint32_t a_sh = buf_sh(a.steps[s].a_buf);
+        const bool a_tmem = h_tmem && a_buf != kBufA;
+        // operands advance by a constant per MMA: two 16-byte k-chunks of A (shared memory: descriptor address field in
+        // 16-byte units; tensor memory: 8 columns) and of W^T
+        uint64_t adesc = tc_smem_desc(buf_sh(a_buf), kTcChunkPitch, 128u);
+        uint32_t a_col = tmem_base + (uint32_t)(a_buf == kBufH1 ? h_col1 : h_col0);
+        const uint64_t b_step = (uint64_t)((2u * (uint32_t)npad * 16u) >> 4);
         tc_mbar_wait(&bar_aready, (uint32_t)(s & 1));  // the A operand is in shared memory, the accumulators are drained
         tc_fence_after();
         MZ_TCCLK(4 * s + 2);
-        for (int k0 = 0; k0 < kpad; k0 += kc0, ++g) {
-          const uint32_t st = g % n_stages, round = g / n_stages;
+        uint32_t acc = 0;
+        for (int k0 = 0; k0 < kpad; k0 += kc0) {
           tc_mbar_wait(&bar_full[st], round & 1u);
           tc_fence_after();
-          const uint32_t b_sh = stages_sh + st * (uint32_t)a.stage_bytes;
+          uint64_t bdesc = tc_smem_desc(stages_sh + st * (uint32_t)stage_bytes, (uint32_t)npad * 16u, 128u);
           const int kc = min(kc0, kpad - k0);
           for (int j = 0; j < kc; j += 16) {
-            // one MMA consumes two 16-byte k-chunks of every row of A and of every row of W^T
-            const uint64_t adesc = tc_smem_desc(a_sh + (uint32_t)((k0 + j) / 8) * kTcChunkPitch, kTcChunkPitch, 128u);
-            const uint64_t bdesc = tc_smem_desc(b_sh + (uint32_t)(j / 8) * (uint32_t)npad * 16u, (uint32_t)npad * 16u, 128u);
-            tc_mma(tmem_base, adesc, bdesc, idesc, (k0 + j) > 0 ? 1u : 0u);
+            if (a_tmem) tc_mma_ts(tmem_base, a_col, bdesc, idesc, acc);
+            else tc_mma(tmem_base, adesc, bdesc, idesc, acc);
+            acc = 1;
+            adesc += (uint64_t)((2u * kTcChunkPitch) >> 4);
+            a_col += 8;
+            bdesc += b_step;
           }
           tc_commit(&bar_empty[st]);  // frees the stage when these MMAs have read it
+          if (++st == n_stages) { st = 0; ++round; }
         }
         tc_commit(&bar_acc);  // the layer's accumulators are complete
         MZ_TCCLK(4 * s + 3);
@@ -357,6 +446,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
     {  // [input row, one-hot(action)] -> A operand (muax/nn.py:105-108); the two halves take alternate 16-byte chunks
       asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: everything above overlapped
                                                            // the kernel that selected (parent, action)
+      if (a.in16 != nullptr) {
+        // bf16 rows: a 16-byte piece of a row IS a k-chunk of the operand.  Lane = (row of an 8-row group, piece mod 4):
+        // one load instruction covers 8 rows x 64 contiguous bytes (8 L1 wavefronts, against 32 for a lane-per-row
+        // walk), one store 8 rows x 16 bytes of 4 adjacent chunks.
+        const int rsub = lane >> 2, q = lane & 3;
+        const int D = a.in_dim, kpad = a.kx16 * 16, full = D / 8, chunks = kpad / 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int rr = warp * 16 + 8 * h + rsub;  // row of the tile
+          const int gb = min(row0 + rr, a.B - 1);
+          const int parent = a.parent != nullptr ? a.parent[gb] : 0;
+          const int action = a.action != nullptr ? a.action[gb] : -1;
+          const __nv_bfloat16* src = a.in16 + (size_t)gb * a.tree16_stride + (size_t)parent * a.es;
+          const uint32_t dst = buf_sh(kBufA) + (uint32_t)rr * 16u;
+          int c = q;
+          for (; c + 28 < full; c += 32) {  // eight pieces in flight
+            uint4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcs(reinterpret_cast<const uint4*>(src) + c + 4 * j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc_sts16(dst + (uint32_t)(c + 4 * j) * kTcChunkPitch, v[j].x, v[j].y, v[j].z, v[j].w);
+          }
+          for (; c < full; c += 4) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + c);
+            tc_sts16(dst + (uint32_t)c * kTcChunkPitch, v.x, v.y, v.z, v.w);
+          }
+          for (; c < chunks; c += 4) {  // the pieces that hold the end of the row, the one-hot action and the padding
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int k = 8 * c + i;
+              v[i] = k < D ? __bfloat162float(src[k]) : ((action >= 0 && k == D + action) ? 1.0f : 0.0f);
+            }
+            tc_sts16(dst + (uint32_t)c * kTcChunkPitch, tc_pack2(v[0], v[1]), tc_pack2(v[2], v[3]), tc_pack2(v[4], v[5]),
+                     tc_pack2(v[6], v[7]));
+          }
+        }
+      } else {
       const int parent = a.parent != nullptr ? a.parent[rb] : 0;
       const int action = a.action != nullptr ? a.action[rb] : -1;
       const int D = a.in_dim;
@@ -395,12 +522,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
         tc_sts16(dst_sh + (uint32_t)(k0 / 8) * kTcChunkPitch, tc_pack2(v[0], v[1]), tc_pack2(v[2], v[3]),
                  tc_pack2(v[4], v[5]), tc_pack2(v[6], v[7]));
       }
+      }
       tc_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) reads
       tc_mbar_arrive(&bar_aready);
       if (tid == 0) MZ_TCCLK(1);
     }
-    for (int s = 0; s < a.n_steps; ++s) {
-      const TcStep& st = a.steps[s];
+    for (int s = 0; s < n_steps; ++s) {
+      const TcStep& st = steps_sh[s];
       const int n = st.n, npad = st.npad;
       const float* bias = bias_all + st.bias_sh;
       // this thread's columns [cb, ce): the layer's columns are split in two halves of whole 32-column groups
@@ -409,7 +537,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
       tc_mbar_wait(&bar_acc, (uint32_t)(s & 1));
       tc_fence_after();
       if (tid == 0) MZ_TCCLK(4 * s + 4);
-      if (st.epi == kEpiHidden) {
+      if (st.epi == kEpiHidden && h_tmem) {
+        const uint32_t h_taddr = trow + (uint32_t)(st.out_buf == kBufH1 ? h_col1 : h_col0);
+        int c0 = cb;
+        for (; c0 + 32 <= ce; c0 += 32) tc_epi_hidden_tmem<32>(trow, c0, bias, a.act_kind, h_taddr);
+        for (; c0 < ce; c0 += 16) tc_epi_hidden_tmem<16>(trow, c0, bias, a.act_kind, h_taddr);
+        tc_wait_st();
+      } else if (st.epi == kEpiHidden) {
         const uint32_t out_sh = buf_sh(st.out_buf) + (uint32_t)r * 16u;
         int c0 = cb;
         for (; c0 + 32 <= ce; c0 += 32) tc_epi_hidden<32>(trow, c0, bias, a.act_kind, out_sh);
@@ -449,7 +583,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
           tc_add_bias<16>(v, bias, c0);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = c0 + i < n ? (v[i] - sub) * inv : 0.0f;
-          if (live) {
+          if (live && a.next_emb != nullptr) {
             if (dst_vec && c0 + 16 <= n) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
@@ -464,6 +598,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
                    tc_pack2(v[4], v[5]), tc_pack2(v[6], v[7]));
           tc_sts16(out_sh + (uint32_t)(c0 / 8 + 1) * kTcChunkPitch, tc_pack2(v[8], v[9]), tc_pack2(v[10], v[11]),
                    tc_pack2(v[12], v[13]), tc_pack2(v[14], v[15]));
+        }
+        if (a.out16 != nullptr) {
+          // the new embedding, bf16, into the tree at [b][next[b]]: the rows now lie in the A operand buffer; the
+          // epilogue warps meet and copy them out with the gather's lane map (8 rows x 64 contiguous bytes per store).
+          // The Prediction layers read the same buffer meanwhile; nothing writes it again.
+          tc_fence_before();
+          tc_fence_proxy_async();
+          tc_mbar_arrive(&bar_aready);  // the next step's MMAs need not wait for the copy
+          asm volatile("bar.sync 1, %0;" ::"r"(kTcEpiThreads) : "memory");
+          const int rsub = lane >> 2, q = lane & 3, pieces = a.es / 8;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int rr = warp * 16 + 8 * h + rsub;
+            if (row0 + rr >= a.B) continue;
+            const int gb = row0 + rr;
+            __nv_bfloat16* dst16 = a.out16 + (size_t)gb * a.tree16_stride + (size_t)a.next[gb] * a.es;
+            const uint32_t src_sh = buf_sh(st.out_buf) + (uint32_t)rr * 16u;
+            for (int c = q; c < pieces; c += 4) {
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(src_sh + (uint32_t)c * kTcChunkPitch));
+              __stcs(reinterpret_cast<uint4*>(dst16) + c, v);
+            }
+          }
+          if (tid == 0) MZ_TCCLK(4 * s + 5);
+          continue;  // already arrived on bar_aready
         }
       } else if (st.epi == kEpiPolicy) {
         for (int c0 = cb; c0 < ce; c0 += 16) {
@@ -550,6 +710,27 @@ __global__ void recurrent_tc_bias_kernel(const float* __restrict__ raw, float* _
     table[dst + c] = c < N ? raw[b_off + c] : 0.0f;
 }
 
+// Root embeddings fp32 [B][E] -> node 0 of the bf16 tree rows (zero padded to es).
+__global__ void recurrent_tc_root16_kernel(const float* __restrict__ root_emb, __nv_bfloat16* __restrict__ emb16, int B,
+                                           int E, int es, int64_t tree_stride) {
+  const long total = (long)B * es;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / es), k = (int)(i - (long)b * es);
+    emb16[(size_t)b * tree_stride + k] = __float2bfloat16_rn(k < E ? root_emb[(size_t)b * E + k] : 0.0f);
+  }
+}
+
+// bf16 tree rows -> the fp32 [B][N][E] embeddings of the mctx tree view.
+__global__ void recurrent_tc_export16_kernel(const __nv_bfloat16* __restrict__ emb16, float* __restrict__ out, long rows,
+                                             int E, int es) {
+  const long total = rows * E;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / E;
+    const int k = (int)(i - r * E);
+    out[i] = __bfloat162float(emb16[r * es + k]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 
 struct TcLayer {
@@ -569,6 +750,9 @@ struct TcImpl {
   __nv_bfloat16* images = nullptr;
   float* bias_table = nullptr;
   size_t image_elems = 0, bias_elems = 0;
+  __nv_bfloat16* emb16 = nullptr;  // [B][N][es] tree embeddings of the throughput mode
+  size_t emb16_elems = 0;
+  int es = 0;
 };
 
 struct TcHead {
@@ -604,7 +788,7 @@ static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& h
       t.a_buf = l == 0 ? kBufA : ((l - 1) & 1 ? kBufH1 : kBufH0);
       t.out_buf = last ? kBufA : (l & 1 ? kBufH1 : kBufH0);
       t.k16 = kpad / 16;
-      t.kc = std::min(kpad, std::max(16, kTcStageBytes / (npad * 2) / 16 * 16));
+      t.kc = 0;  // set below, once the stage size is known
       t.n = N;
       t.npad = npad;
       t.epi = last ? h.final_epi : kEpiHidden;
@@ -627,16 +811,42 @@ static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& h
   a.bufA_bytes = bufA_k / 8 * (int)kTcChunkPitch;
   a.bufH_bytes = max_hidden_pad / 8 * (int)kTcChunkPitch;
   a.bufH1_bytes = deepest >= 3 ? a.bufH_bytes : 0;
-  a.stage_bytes = kTcStageBytes;
   a.bias_floats = bias_floats;
+  int need_cols = max_npad;
+  a.h_tmem = 0;
+  // default on (bit-identical results; 133 against 160 cycles per N = 256 MMA and 64 KB of shared memory back for the
+  // weight ring); MZ_TC_TMEM_H=0 keeps the hidden activations in shared memory
+  static const bool want_h_tmem = getenv("MZ_TC_TMEM_H") == nullptr || atoi(getenv("MZ_TC_TMEM_H")) != 0;
+  if (want_h_tmem && deepest >= 2) {
+    // hidden activations in tensor memory: 16 accumulator-aligned columns per 32 hidden units, after the accumulators
+    const int hcols = round_up(max_hidden_pad / 2, 16);
+    const int total = round_up(max_npad, 16) + hcols * (deepest >= 3 ? 2 : 1);
+    if (total <= 512) {
+      a.h_tmem = 1;
+      a.h_col[0] = round_up(max_npad, 16);
+      a.h_col[1] = a.h_col[0] + hcols;
+      need_cols = total;
+      a.bufH_bytes = 0;
+      a.bufH1_bytes = 0;
+    }
+  }
   int cols = 32;
-  while (cols < max_npad) cols <<= 1;
+  while (cols < need_cols) cols <<= 1;
   a.tmem_cols = cols;
   const size_t fixed = (size_t)a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes + (size_t)bias_floats * 4 + 128;
   const size_t budget = (size_t)max_smem - 2048;
-  if (fixed + 2 * (size_t)kTcStageBytes > budget) return fail("operands do not fit shared memory");
-  a.n_stages = (int)std::min<size_t>(kTcMaxStages, (budget - fixed) / kTcStageBytes);
-  prog.smem = fixed + (size_t)a.n_stages * kTcStageBytes;
+  // stage size: 32 KB (four MMAs per wait / commit at N = 256; C5: 3.01 against 3.09 ms per act) when at least four such
+  // stages fit, else 16 KB
+  a.stage_bytes = tc_stage_env() != 0 ? tc_stage_env()
+                                      : (fixed + 4 * (size_t)(2 * kTcStageBytes) <= budget ? 2 * kTcStageBytes : kTcStageBytes);
+  if (fixed + 2 * (size_t)a.stage_bytes > budget) return fail("operands do not fit shared memory");
+  a.n_stages = (int)std::min<size_t>(kTcMaxStages, (budget - fixed) / a.stage_bytes);
+  prog.smem = fixed + (size_t)a.n_stages * a.stage_bytes;
+  for (int i = 0; i < n_steps; ++i) {
+    TcStep& t = a.steps[i];
+    t.kc = std::min(t.k16 * 16, std::max(16, a.stage_bytes / (t.npad * 2) / 16 * 16));
+    impl->layers[layers0 + i].kc = t.kc;
+  }
   *bias_base += bias_floats;
   prog.ok = true;
   return true;
@@ -716,6 +926,7 @@ void recurrent_tc_destroy(RecurrentTcState& st) {
   if (impl != nullptr) {
     if (impl->images) cudaFree(impl->images);
     if (impl->bias_table) cudaFree(impl->bias_table);
+    if (impl->emb16) cudaFree(impl->emb16);
     delete impl;
   }
   st.impl = nullptr;
@@ -780,6 +991,73 @@ int recurrent_tc_launch(RecurrentTcState& st, const Net& net, const Tree& t, con
   a.logits = logits;
   a.next_emb = next_emb;
   return tc_run(impl->rec, a, t.B, stream, launches, err);
+}
+
+int recurrent_tc_tree_begin(RecurrentTcState& st, const Net& net, int B, int N, const float* root_emb, bool clear,
+                            cudaStream_t stream, int64_t* launches, std::string* err) {
+  TcImpl* impl = static_cast<TcImpl*>(st.impl);
+  const int E = net.embed_dim, es = round_up(E, 8);
+  const size_t need = (size_t)B * N * es;
+  if (need > impl->emb16_elems) {
+    if (impl->emb16) cudaFree(impl->emb16);
+    impl->emb16 = nullptr;
+    impl->emb16_elems = 0;
+    if (cudaMalloc((void**)&impl->emb16, need * sizeof(__nv_bfloat16) + 16) != cudaSuccess) {
+      cudaGetLastError();
+      *err = "recurrent_tc: cudaMalloc(bf16 tree embeddings) failed";
+      return 1;
+    }
+    impl->emb16_elems = need;
+  }
+  impl->es = es;
+  if (clear && cudaMemsetAsync(impl->emb16, 0, need * sizeof(__nv_bfloat16), stream) != cudaSuccess) {
+    *err = "recurrent_tc: cudaMemsetAsync(bf16 tree embeddings) failed";
+    return 1;
+  }
+  const long total = (long)B * es;
+  recurrent_tc_root16_kernel<<<(unsigned)std::min<long>((total + 255) / 256, 4096), 256, 0, stream>>>(
+      root_emb, impl->emb16, B, E, es, (int64_t)N * es);
+  *launches += 1;
+  return 0;
+}
+
+int recurrent_tc_tree_launch(RecurrentTcState& st, const Net& net, int B, int N, const int32_t* parent,
+                             const int32_t* action, const int32_t* next, float* reward, float* value, float* logits,
+                             cudaStream_t stream, int64_t* launches, std::string* err) {
+  (void)net;
+  TcImpl* impl = static_cast<TcImpl*>(st.impl);
+  TcArgs a = impl->rec.args;
+  a.in = nullptr;
+  a.in_row_stride = 0;
+  a.in16 = impl->emb16;
+  a.out16 = impl->emb16;
+  a.next = next;
+  a.tree16_stride = (int64_t)N * impl->es;
+  a.es = impl->es;
+  a.parent = parent;
+  a.action = action;
+  a.reward = reward;
+  a.value = value;
+  a.logits = logits;
+  a.next_emb = nullptr;
+  return tc_run(impl->rec, a, B, stream, launches, err);
+}
+
+int recurrent_tc_tree_export(RecurrentTcState& st, const Net& net, int B, int N, float* embeddings, cudaStream_t stream,
+                             std::string* err) {
+  TcImpl* impl = static_cast<TcImpl*>(st.impl);
+  if (impl == nullptr || impl->emb16 == nullptr) {
+    *err = "recurrent_tc: no bf16 tree to export";
+    return 1;
+  }
+  const long rows = (long)B * N;
+  recurrent_tc_export16_kernel<<<(unsigned)std::min<long>((rows * net.embed_dim + 255) / 256, 8192), 256, 0, stream>>>(
+      impl->emb16, embeddings, rows, net.embed_dim, impl->es);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) {
+    *err = "recurrent_tc: exporting the bf16 tree embeddings failed";
+    return 1;
+  }
+  return 0;
 }
 
 bool recurrent_tc_has_root(const RecurrentTcState& st, bool from_obs) {

@@ -29,6 +29,18 @@ int recurrent_tc_launch(RecurrentTcState& st, const Net& net, const Tree& t, con
                         const int32_t* action, float* reward, float* value, float* logits, float* next_emb,
                         cudaStream_t stream, int64_t* launches, std::string* err);
 
+// The search of the throughput mode keeps its tree embeddings in bf16 (the precision the tensor core reads them in):
+// rows [B][N][E rounded up to 8], so that gathering a parent row and storing the next state are plain 16-byte copies
+// to / from the operand buffer.  begin: (re)allocate, node 0 = bf16(root_emb); launch: recurrent_fn from
+// [b][parent[b]] + action[b], next state stored at [b][next[b]]; export: the fp32 [B][N][E] array of the tree view.
+int recurrent_tc_tree_begin(RecurrentTcState& st, const Net& net, int B, int N, const float* root_emb, bool clear,
+                            cudaStream_t stream, int64_t* launches, std::string* err);
+int recurrent_tc_tree_launch(RecurrentTcState& st, const Net& net, int B, int N, const int32_t* parent,
+                             const int32_t* action, const int32_t* next, float* reward, float* value, float* logits,
+                             cudaStream_t stream, int64_t* launches, std::string* err);
+int recurrent_tc_tree_export(RecurrentTcState& st, const Net& net, int B, int N, float* embeddings, cudaStream_t stream,
+                             std::string* err);
+
 // `_root_inference` (muax/model.py:251-263) on the same kernel: from observations (Representation -> emb_out, value,
 // prior logits) or from a caller-made embedding (value, prior logits).  Only when recurrent_tc_has_root says so.
 bool recurrent_tc_has_root(const RecurrentTcState& st, bool from_obs);

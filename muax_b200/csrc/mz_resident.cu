@@ -474,15 +474,15 @@ namespace mz {
 
 // One thread per (tree, simulation) of the simulations [sim0, sim1): per-tree key = split(sim_key, B_global)[global
 // row]; then per level (key, sel) = split(key); noise[a] = 1e-7 * uniform(sel, (A,))[a]  (Appendix A.3, A.5, A.7).
-// Row = K levels x A.  Simulation-major (a warp works on one simulation of 32 trees), so the level bound is
-// warp-uniform: simulation s walks a tree of s + 1 nodes, its path has at most s + 1 levels (and then never reaches the
-// continuation key, which is only read at depth K).
+// Row = K levels x A.  Tree-major (a warp works on 32 consecutive simulations of one tree: their rows are adjacent in
+// the table).  Simulation s walks a tree of s + 1 nodes: its path has at most s + 1 levels (and then never reaches the
+// continuation key, which is only read at depth K), so only the first min(K, s + 1) levels are produced.
 __global__ void __launch_bounds__(128) resident_noise_kernel(SearchParams p, int B, int A, int K, int sim0, int sim1,
                                                              float* __restrict__ table, uint32_t* __restrict__ cont) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int NS = p.num_simulations;
-  if (idx >= B * (sim1 - sim0)) return;
-  const int sim = sim0 + idx / B, b = idx % B;
+  const int NS = p.num_simulations, nsim = sim1 - sim0;
+  if (idx >= B * nsim) return;
+  const int b = idx / nsim, sim = sim0 + idx % nsim;
   const size_t pair = (size_t)b * NS + sim;
   uint32_t k0, k1;
   split_key(p.sim_keys[2 * sim], p.sim_keys[2 * sim + 1], (uint32_t)p.global_batch, (uint32_t)(p.batch_offset + b),

@@ -312,6 +312,7 @@ struct mz_handle {
   // scratch
   int32_t *sel_parent = nullptr, *sel_action = nullptr, *sel_next = nullptr;
   int32_t* sel5 = nullptr;  // 5 x B scratch of the batched tree-warp kernels (throughput mode)
+  bool tree16 = false;      // the last search kept its embeddings in the tcgen05 kernel's bf16 rows (mz_get_tree exports them)
   float *rec_reward = nullptr, *rec_value = nullptr, *rec_logits = nullptr, *rec_emb = nullptr;
   float *root_logits = nullptr, *root_value = nullptr, *root_emb = nullptr;
   uint32_t* sim_keys_dev = nullptr;
@@ -401,6 +402,10 @@ static int check_args(const mz_handle* h, const mz_search_args* a) {
   if (a->policy != MZ_POLICY_MUZERO && a->policy != MZ_POLICY_GUMBEL) return fail_arg("unknown policy");
   if (a->qtransform != 0 && a->qtransform != 1) return fail_arg("unknown qtransform");
   if (a->precision != MZ_PRECISION_FP32 && a->precision != MZ_PRECISION_BF16) return fail_arg("unknown precision");
+  if (a->num_decision_actions < 0 || a->num_decision_actions >= h->cfg.num_actions)
+    return fail_arg("num_decision_actions must be in [0, num_actions)");
+  if (a->num_decision_actions > 0 && a->policy != MZ_POLICY_MUZERO)
+    return fail_arg("num_decision_actions (stochastic MuZero) needs policy = MZ_POLICY_MUZERO");
   if (a->num_simulations < 0 || a->num_simulations > h->cfg.max_num_simulations)
     return fail_arg("num_simulations exceeds the handle's max_num_simulations");
   if (a->policy == MZ_POLICY_GUMBEL && (a->max_considered < 0 || a->max_considered > 1024))
@@ -435,6 +440,7 @@ static int stage_keys(mz_handle* h, const mz_search_args* a, cudaStream_t stream
   p.value_scale = a->value_scale;
   p.maxvisit_init = a->maxvisit_init;
   p.discount = h->cfg.discount;
+  p.stoch_A = a->num_decision_actions;
   const uint32_t rng[2] = {a->key0, a->key1};
   uint32_t search_key[2], aux[2], fin[2] = {0, 0};
   if (a->policy == MZ_POLICY_MUZERO) {  // rng_key, dirichlet_key, search_key = split(rng_key, 3)
@@ -588,15 +594,19 @@ static int search_tc(mz_handle* h, const float* obs, const float* root_logits, c
                              noise, h->sel5, stream, &h->launches, &err))
     return fail(err);
   const int B = h->cfg.batch;
+  // tree embeddings in bf16 (what the tensor core reads): the recurrent kernel gathers and stores them itself
+  const bool clear16 = h->params.max_depth > 0 || NS + 1 < h->N;
+  if (recurrent_tc_tree_begin(h->rtc, h->net, B, h->N, root_emb, clear16, stream, &h->launches, &err)) return fail(err);
   for (int sim = 0; sim < NS; ++sim) {
     if (treewarp_batched_select(h->treewarp, sim, stream, &h->launches, &err)) return fail(err);
-    if (recurrent_tc_launch(h->rtc, h->net, h->tree, h->sel5, h->sel5 + B, h->rec_reward, h->rec_value, h->rec_logits,
-                            h->rec_emb, stream, &h->launches, &err))
+    if (recurrent_tc_tree_launch(h->rtc, h->net, B, h->N, h->sel5, h->sel5 + B, h->sel5 + 2 * B, h->rec_reward,
+                                 h->rec_value, h->rec_logits, stream, &h->launches, &err))
       return fail(err);
-    if (treewarp_batched_backup(h->treewarp, h->rec_reward, h->rec_value, h->rec_logits, h->rec_emb, stream,
+    if (treewarp_batched_backup(h->treewarp, h->rec_reward, h->rec_value, h->rec_logits, nullptr, stream,
                                 &h->launches, &err))
       return fail(err);
   }
+  h->tree16 = true;
   if (treewarp_batched_finish(h->treewarp, action_out, weights_out, stream, &h->launches, &err)) return fail(err);
   return 0;
 }
@@ -658,10 +668,14 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
     return fail_arg("root_logits and root_value must be given together");
   if (obs != nullptr && h->cfg.obs_dim <= 0)
     return fail_arg("handle was created with obs_dim = 0: supply the root embedding instead of obs");
+  if (args->num_decision_actions > 0)
+    return fail_arg("stochastic MuZero (num_decision_actions > 0) runs in the callback mode: mz_begin / mz_select / "
+                    "mz_expand_backup / mz_finish");
   MZ_CUDA(cudaSetDevice(h->cfg.device));
   if (int rc = stage_keys(h, args, stream)) return rc;
   h->resident.dirty = false;  // whatever runs next owns the SoA tree view
   h->tree_valid = false;
+  h->tree16 = false;
   const bool want_tree = (args->flags & MZ_FLAG_WANT_TREE) != 0;
   MZ_CUDA(cudaEventRecord(h->ev_start, stream));
   int engine = args->engine;
@@ -772,6 +786,7 @@ void mz_default_args(mz_search_args* a) {
   a->engine = MZ_ENGINE_AUTO;
   a->flags = 0;  // no tree view unless asked for (MZ_FLAG_WANT_TREE): muax never reads PolicyOutput.search_tree
   a->precision = MZ_PRECISION_FP32;
+  a->num_decision_actions = 0;
 }
 
 int mz_create(mz_handle** out, const mz_config* cfg) {
@@ -1102,6 +1117,11 @@ int mz_get_tree(mz_handle* h, mz_tree_view* v) {
   {  // the CTA-resident engine keeps packed records; the mctx SoA view is produced when somebody asks for it
     std::string err;
     if (mz::resident_unpack(h->resident, t, h->cfg.discount, &err)) return mz::fail(err);
+    if (h->tree16) {  // throughput mode: the embeddings live in bf16 rows
+      if (mz::recurrent_tc_tree_export(h->rtc, h->net, t.B, t.N, t.embeddings, h->resident.last_stream, &err))
+        return mz::fail(err);
+      h->tree16 = false;  // exported once; the fp32 view stays valid until the next search
+    }
   }
   v->batch = t.B;
   v->num_nodes = t.N;

@@ -126,12 +126,12 @@ class SearchEngine:
                   max_depth=None, dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25, pb_c_base=19652,
                   max_num_considered_actions=16, gumbel_scale=1.0, value_scale=0.1, maxvisit_init=50.0,
                   global_batch=None, batch_offset=0, engine=_lib.ENGINE_AUTO, want_tree=False,
-                  precision=_lib.PRECISION_FP32):
+                  precision=_lib.PRECISION_FP32, num_decision_actions=0):
         # a 0.45 ms search makes the host call path matter: the argument struct is built once per distinct keyword
         # set and only the key words change from act to act
         ck = (policy, qtransform, num_simulations, temperature, max_depth, dirichlet_fraction, dirichlet_alpha,
               pb_c_init, pb_c_base, max_num_considered_actions, gumbel_scale, value_scale, maxvisit_init, global_batch,
-              batch_offset, engine, want_tree, precision)
+              batch_offset, engine, want_tree, precision, num_decision_actions)
         cached = self._args_cache.get(ck)
         if cached is not None:
             cached.key0, cached.key1 = key_words(rng_key)
@@ -150,6 +150,7 @@ class SearchEngine:
         a.engine = engine
         a.flags = _lib.FLAG_WANT_TREE if want_tree else 0
         a.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}.get(precision, precision)
+        a.num_decision_actions = int(num_decision_actions)
         a.temperature, a.dirichlet_fraction, a.dirichlet_alpha = temperature, dirichlet_fraction, dirichlet_alpha
         a.pb_c_init, a.pb_c_base, a.gumbel_scale = pb_c_init, pb_c_base, gumbel_scale
         a.value_scale, a.maxvisit_init = value_scale, maxvisit_init

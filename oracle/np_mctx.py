@@ -497,6 +497,93 @@ def gumbel_muzero_policy(model, key, root, num_simulations, invalid_actions=None
     return dict(action=action, action_weights=w, tree=tree, sim_depth=depths, root_noise=gumbel)
 
 
+# ---------------------------------------------------------------------------------- stochastic MuZero
+# mctx.stochastic_muzero_policy (call site: muax/policy.py:50-67; skeleton of the afterstate search visible in-tree
+# at muax/frameworks/acme/jax/diffusion_muzero/policy.py:77-129,150-211).  PARITY UNPINNED like the rest of this
+# module (mctx is absent): restated from the published algorithm — the tree holds A' = A + C pseudo-actions; the
+# embedding of a node is (state, afterstate, is_decision); `stochastic_recurrent_fn` evaluates BOTH the decision and the
+# chance function for every row and keeps one by the PARENT's node type; decision nodes select with pUCT over all A'
+# slots (chance slots carry -inf priors), chance nodes with argmax softmax(prior) / (visits + 1); Dirichlet noise,
+# the invalid-action mask, the visit summary and the final draw see the A decision actions only.  Root invalid actions
+# are padded with zeros for the chance slots (their -inf prior already keeps them out).
+
+class StochasticModel:
+    """Adapter with Model's `recurrent_inference(action, emb)` surface over a (decision_fn, chance_fn) pair.
+    decision_fn(action[B], state[B, Es]) -> (chance_logits[B, C], afterstate_value[B], afterstate[B, Ea]);
+    chance_fn(outcome[B], afterstate[B, Ea]) -> (action_logits[B, A], value[B], reward[B], discount[B], state[B, Es]).
+    Flat embedding layout: [state (Es) | afterstate (Ea) | is_decision (1)]."""
+
+    def __init__(self, math, decision_fn, chance_fn, num_actions, num_chance, state_dim, afterstate_dim):
+        self.m = math
+        self.decision_fn, self.chance_fn = decision_fn, chance_fn
+        self.A, self.C, self.Es, self.Ea = num_actions, num_chance, state_dim, afterstate_dim
+
+    def root_embedding(self, state):
+        B = state.shape[0]
+        _, _, after = self.decision_fn(np.zeros(B, np.int32), state)  # mctx builds a dummy afterstate the same way
+        return np.concatenate([state, after, np.ones((B, 1), F32)], axis=1).astype(F32)
+
+    def recurrent_inference(self, action, emb):
+        B = emb.shape[0]
+        state, after, is_dec = emb[:, :self.Es], emb[:, self.Es:self.Es + self.Ea], emb[:, -1] != 0
+        chance_logits, after_value, new_after = self.decision_fn(action, state)
+        act_logits, value, reward, discount, new_state = self.chance_fn(action - self.A, after)
+        ninf = lambda n: np.full((B, n), -np.inf, F32)  # noqa: E731
+        logits = np.where(is_dec[:, None], np.concatenate([ninf(self.A), chance_logits], 1),
+                          np.concatenate([act_logits, ninf(self.C)], 1)).astype(F32)
+        v = np.where(is_dec, after_value, value).astype(F32)
+        r = np.where(is_dec, F32(0), reward).astype(F32)
+        d = np.where(is_dec, F32(1), discount).astype(F32)
+        new_emb = np.concatenate([new_state, new_after, (~is_dec).astype(F32)[:, None]], axis=1).astype(F32)
+        return r, d, logits, v, new_emb
+
+
+def stochastic_muzero_policy(model, key, root, num_simulations, invalid_actions=None, max_depth=None, qtransform=0,
+                             dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25, pb_c_base=19652.0,
+                             temperature=1.0, mode=tf.LEGACY, dirichlet_noise=None):
+    """root = (prior_logits[B, A], value[B], state[B, Es]); model = StochasticModel."""
+    m = model.m
+    logits, value, state = root
+    B, A = logits.shape
+    C = model.C
+    rng_key, _dirichlet_key, search_key = tf.split(np.asarray(key, np.uint32), 3, mode)
+    probs = softmax(m, logits)
+    if dirichlet_noise is None:
+        from . import c_oracle
+        dirichlet_noise = c_oracle.dirichlet(_dirichlet_key, 0, B, A, dirichlet_alpha)
+    noise = np.asarray(dirichlet_noise, F32)
+    noisy = ((F32(1) - F32(dirichlet_fraction)) * probs + F32(dirichlet_fraction) * noise).astype(F32)
+    new_logits = mask_invalid_actions(m.log(np.maximum(noisy, TINY)), invalid_actions)
+    new_logits = np.concatenate([new_logits, np.full((B, C), -np.inf, F32)], axis=1)
+    invalid_padded = None if invalid_actions is None else np.concatenate(
+        [np.asarray(invalid_actions).astype(np.uint8), np.zeros((B, C), np.uint8)], axis=1)
+    qt = QTRANSFORMS[qtransform]
+
+    def sel(keys, tree, rows, node, depth):
+        decision = muzero_action_selection(m, keys, tree, rows, node, depth, qt, pb_c_init, pb_c_base, mode)
+        prob = softmax(m, tree.children_prior_logits[rows, node])
+        chance = np.argmax((prob / (tree.children_visits[rows, node] + 1).astype(F32)).astype(F32), axis=-1)
+        is_dec = tree.embeddings[rows, node, -1] != 0
+        return np.where(is_dec, decision, chance).astype(np.int32)
+
+    with np.errstate(invalid="ignore"):  # -inf - -inf inside softmax of fully masked slots never happens; inf * 0 may
+        tree, depths = search(model, search_key, (new_logits, value, model.root_embedding(np.asarray(state, F32))),
+                              num_simulations, max_depth, invalid_padded, sel, sel, mode)
+    vc = tree.children_visits[:, ROOT, :A].astype(F32)
+    total = np.zeros(B, F32)
+    for a in range(A):
+        total = (total + vc[:, a]).astype(F32)
+    total = total[:, None]
+    w = np.where(total > 0, (vc / np.maximum(total, F32(1))).astype(F32), F32(1 / A)).astype(F32)
+    l = m.log(np.maximum(w, TINY))
+    l = (l - l.max(axis=-1, keepdims=True)).astype(F32)
+    l = (l / np.maximum(TINY, F32(temperature))).astype(F32)
+    u = tf.uniform_tiny(rng_key, B * A, mode).reshape(B, A)
+    g = (-m.log((-m.log(u)).astype(F32))).astype(F32)
+    action = np.argmax((g + l).astype(F32), axis=-1).astype(np.int32)
+    return dict(action=action, action_weights=w, tree=tree, sim_depth=depths, root_noise=noise)
+
+
 def act(nets, key, obs=None, root=None, math=None, policy=0, invalid=None, noise=None, support_size=10,
         discount=0.99, activation=0, repr_minmax=1, dyn_minmax=1, prng_mode=tf.LEGACY, num_simulations=5,
         max_depth=None, qtransform=0, max_considered=16, gumbel_scale=1.0, temperature=1.0, dirichlet_fraction=0.25,

@@ -159,4 +159,6 @@ def test_batched_tree_kernels_equal_the_stepwise_kernels(obs_dim, E, A, S, hidde
     for g, w in zip(res["batched"][0], res["stepwise"][0]):
         assert np.array_equal(g, w)
     for k, w in res["stepwise"][1].items():
+        if k == "embeddings":  # the throughput mode keeps its embeddings in bf16 (what the tensor core reads anyway)
+            w = _bf16(w).astype(np.float32)
         assert np.array_equal(res["batched"][1][k], w), k
