@@ -275,6 +275,7 @@ def build_model(wl, nets, dev):
     E, A, F = wl["E"], wl["A"], 2 * wl["S"] + 1
     if wl.get("conv"):
         from muax_b200.conv import ResNetRepresentation
+        torch.backends.cudnn.benchmark = True  # fixed shapes: let cuDNN pick its fastest convolution algorithms
         torch.manual_seed(0)
         H, W, C = wl["conv"]
         conv = ResNetRepresentation(E, frame_channels=C, height=H, width=W).to(dev).eval()
@@ -369,10 +370,9 @@ def run_ours(args, wl, name):
 
     def step_host(i):
         key = np.array([0, i], np.uint32)
-        a, pi, v = model.act(key, obs_host, with_pi=True, with_value=True, obs_from_batch=True, **act_kw, **my_rows)
-        if world > 1:  # the exchange, synchronously: results of every rank on every rank
-            sharded.gather_host(a, pi, v)
-        return a
+        if world > 1:  # NumPy in, NumPy out, results of every rank on every rank: search + all-gather + one D2H
+            return sharded.act_host(key, obs_host)[0]
+        return model.act(key, obs_host, with_pi=True, with_value=True, obs_from_batch=True, **act_kw, **my_rows)[0]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -490,10 +490,12 @@ def run_ours(args, wl, name):
                                   "the same steps",
                         "wall_s_incl_flush": wall},
             "e2e": {"value": e2e, "unit": "sims/s", "h2d_bytes_per_step": int(obs_host.nbytes),
-                    "d2h_bytes_per_step": int(B * (4 + 4 * A + 4)), "ms_per_step": host_total_ms / args.steps,
-                    "api": "MuZero.act(key, obs, with_pi=True, with_value=True, obs_from_batch=True): NumPy observations "
-                           "in, NumPy (action, action_weights, root_value) out, one stream sync"
-                           + ("; then the all-gather of the three arrays" if world > 1 else "")},
+                    "d2h_bytes_per_step": int(GB * (4 + 4 * A + 4)), "ms_per_step": host_total_ms / args.steps,
+                    "api": ("MuZero.act(key, obs, with_pi=True, with_value=True, obs_from_batch=True): NumPy observations "
+                            "in, NumPy (action, action_weights, root_value) out, one stream sync") if world == 1 else
+                           ("ShardedSearch.act_host(key, obs): NumPy observations of this rank's rows in, NumPy (action, "
+                            "action_weights, root_value) of ALL ranks' rows out: pinned H2D, MuZero.act_device, NCCL "
+                            "all-gather, one D2H, one stream sync")},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": "sims/s", "cores": threads, "kind": "port",

@@ -46,10 +46,15 @@ class ResNetRepresentation(nn.Module):
         self.project = nn.Linear(n, embedding_dim)
         self.embedding_dim = embedding_dim
 
+    supports_bf16 = True  # MuZero._plan passes bf16=True in the throughput mode (precision="bf16")
+
     @torch.no_grad()
-    def forward(self, obs):
-        x = obs.to(torch.float32) / 255.0
-        x = self.torso(x.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last))
+    def forward(self, obs, bf16=False):
+        """uint8 frames stay uint8 until they are on the device (a quarter of the float32 H2D bytes); bf16=True runs
+        the convolutions under autocast (tensor cores; the normalisations stay fp32)."""
+        x = obs.permute(0, 3, 1, 2).to(torch.float32, memory_format=torch.channels_last) / 255.0
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(bf16) and x.is_cuda):
+            x = self.torso(x).to(torch.float32)
         # min_max_normalize2d (muax/nn.py:48-56): per sample and channel over the spatial positions
         lo, hi = x.amin(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)
         scale = hi - lo

@@ -232,7 +232,11 @@ class MuZero:
             loop_fn=None, qtransform=None, dirichlet_fraction: float = 0.25, dirichlet_alpha: float = 0.3,
             pb_c_init: float = 1.25, pb_c_base: float = 19652, **extra):
         """Same contract as muax/model.py:82-179 (`loop_fn` is accepted and ignored: there is no tracing)."""
-        obs = np.asarray(obs, dtype=np.float32) if not isinstance(obs, torch.Tensor) else obs
+        if not isinstance(obs, torch.Tensor):
+            # uint8 frames for a torch (conv) Representation travel as uint8: a quarter of the H2D bytes and no host
+            # conversion pass; everything else becomes float32 like in the reference
+            keep_u8 = self._hybrid and isinstance(obs, np.ndarray) and obs.dtype == np.uint8
+            obs = obs if keep_u8 else np.asarray(obs, dtype=np.float32)
         if not obs_from_batch:
             obs = obs[None]
         if invalid_actions is not None and not obs_from_batch and np.ndim(invalid_actions) == 1:
@@ -262,7 +266,9 @@ class MuZero:
         `out=(action, weights, root_value)`: preallocated tensors the search kernel writes into (native nets only)."""
         if not isinstance(obs, torch.Tensor) or not obs.is_cuda:
             raise ValueError("act_device expects a CUDA tensor; use act() for host observations")
-        plan_output, root_value = self._plan(self._params, rng_key, obs.to(torch.float32), num_simulations=num_simulations,
+        if not (self._hybrid and obs.dtype == torch.uint8):
+            obs = obs.to(torch.float32)
+        plan_output, root_value = self._plan(self._params, rng_key, obs, num_simulations=num_simulations,
                                              temperature=temperature, **kw)
         return plan_output.action, plan_output.action_weights, root_value
 
@@ -280,7 +286,12 @@ class MuZero:
             # root Representation in torch (once per act), then the native search from root = (None, None, embedding):
             # the library runs Prediction on the embedding and everything inside the simulation loop
             dev = torch.device("cuda") if self._device is None else torch.device(self._device)
-            emb = self._fns.representation_fn(torch.as_tensor(obs, device=dev))
+            rep = self._fns.representation_fn
+            obs_t = torch.as_tensor(obs, device=dev)
+            if getattr(rep, "supports_bf16", False) and extra.get("precision") in ("bf16", _lib.PRECISION_BF16):
+                emb = rep(obs_t, bf16=True)
+            else:
+                emb = rep(obs_t)
             emb = emb.reshape(emb.shape[0], -1).to(torch.float32).contiguous()
             engine = self._engine_for(emb.shape[0], num_simulations, params)
             kw = self._policy._search_kwargs(kwargs)

@@ -132,8 +132,106 @@ class GumbelMuZeroPolicy(_EnginePolicy):  # muax/policy.py:33-47
             precision=kwargs.get("precision", _lib.PRECISION_FP32))
 
 
-class StochasticMuZeroPolicy(Policy):  # muax/policy.py:50-67 — SURVEY.md §8(f) rank 3, not built yet
+class DecisionRecurrentFnOutput(NamedTuple):  # mctx.DecisionRecurrentFnOutput
+    chance_logits: Any
+    afterstate_value: Any
+
+
+class ChanceRecurrentFnOutput(NamedTuple):  # mctx.ChanceRecurrentFnOutput
+    action_logits: Any
+    value: Any
+    reward: Any
+    discount: Any
+
+
+class StochasticMuZeroPolicy(Policy):  # muax/policy.py:50-67 (mctx.stochastic_muzero_policy)
+    """Afterstate / chance-node search.  The tree kernels run in the library (callback mode) on A' = A + C
+    pseudo-actions: decision nodes (even depth) select with pUCT over the A' slots, chance nodes (odd depth) with
+    `argmax prior / (visits + 1)`; Dirichlet noise, the invalid-action mask, the visit summary and the final draw see
+    the A decision actions only.  The two recurrent functions are torch callables with mctx's signatures:
+
+        decision_recurrent_fn(params, rng_key, action i32[B], state_embedding[B, Es])
+            -> (DecisionRecurrentFnOutput(chance_logits[B, C], afterstate_value[B]), afterstate_embedding[B, Ea])
+        chance_recurrent_fn(params, rng_key, chance_outcome i32[B], afterstate_embedding[B, Ea])
+            -> (ChanceRecurrentFnOutput(action_logits[B, A], value[B], reward[B], discount[B]), state_embedding[B, Es])
+
+    As in mctx both are evaluated for every row of a simulation and one result is kept by the parent's node type (the
+    index a row does not use is clamped into range instead of relying on XLA's out-of-range gather).  The node
+    embedding is the flat row [state | afterstate | is_decision]."""
+
+    def __init__(self, discount=1.0, prng_mode=_lib.PRNG_LEGACY):
+        self._engines = {}
+        self._discount, self._prng_mode = discount, prng_mode
+
+    def _engine(self, B, A2, E2, num_simulations, device):
+        import numpy as np
+
+        from .nn import pack_stacks
+        from .search import SearchEngine
+        key = (B, A2, E2, str(device))
+        eng = self._engines.get(key)
+        if eng is None or eng.max_num_simulations < num_simulations:
+            z = lambda i, o: [(np.zeros((i, o), np.float32), np.zeros(o, np.float32))]  # noqa: E731
+            _, cstacks = pack_stacks(dict(pred_v=z(E2, 1), pred_pi=z(E2, A2), dyn_ns=z(E2 + A2, E2), dyn_r=z(E2 + A2, 1)))
+            if eng is not None:
+                eng.close()
+            eng = SearchEngine(cstacks, batch=B, num_actions=A2, embed_dim=E2, obs_dim=0, support_size=0,
+                               max_num_simulations=max(int(num_simulations), 1), discount=self._discount,
+                               prng_mode=self._prng_mode, device=device)
+            self._engines[key] = eng
+        return eng
+
     def __call__(self, params, rng_key, root, recurrent_fn=None, decision_recurrent_fn=None,
                  chance_recurrent_fn=None, **kwargs):
-        raise NotImplementedError("StochasticMuZeroPolicy (afterstate / chance-node search) is outside the "
-                                  "accelerated hot path; see DESIGN.md 'out of scope'")
+        import torch
+        if decision_recurrent_fn is None or chance_recurrent_fn is None:
+            raise ValueError("StochasticMuZeroPolicy needs decision_recurrent_fn and chance_recurrent_fn")
+        dev = kwargs.get("device")
+        f32 = torch.float32
+
+        def t(x, dtype=f32):
+            x = x if isinstance(x, torch.Tensor) else torch.as_tensor(x)
+            return x.to(device=dev if dev is not None else (x.device if x.is_cuda else "cuda"), dtype=dtype)
+
+        logits, value, state = t(root.prior_logits), t(root.value), t(root.embedding)
+        dev = logits.device
+        B, A = logits.shape
+        Es = state.shape[1]
+        dummy, after0 = decision_recurrent_fn(params, None, torch.zeros(B, dtype=torch.int32, device=dev), state)
+        C, Ea = int(dummy.chance_logits.shape[-1]), int(after0.shape[1])
+        A2, E2 = A + C, Es + Ea + 1
+        num_simulations = kwargs.get("num_simulations", 5)
+        engine = self._engine(B, A2, E2, num_simulations, dev)
+        ninf = lambda n: torch.full((B, n), float("-inf"), dtype=f32, device=dev)  # noqa: E731
+        zeros = lambda n, dt=f32: torch.zeros((B, n), dtype=dt, device=dev)  # noqa: E731
+        root2 = (torch.cat([logits, zeros(C)], 1), value,
+                 torch.cat([state, t(after0), torch.ones((B, 1), dtype=f32, device=dev)], 1))
+        invalid = kwargs.get("invalid_actions")
+        if invalid is not None:
+            invalid = torch.cat([t(invalid, torch.uint8), zeros(C, torch.uint8)], 1)
+        noise = kwargs.get("noise")
+        if noise is not None:
+            noise = torch.cat([t(noise), zeros(C)], 1)
+
+        def step(action, emb):
+            st, af, is_dec = emb[:, :Es], emb[:, Es:Es + Ea], emb[:, -1] != 0
+            dec, new_af = decision_recurrent_fn(params, None, action.clamp(max=A - 1), st)
+            ch, new_st = chance_recurrent_fn(params, None, (action - A).clamp(min=0), af)
+            p_logits = torch.where(is_dec[:, None], torch.cat([ninf(A), t(dec.chance_logits)], 1),
+                                   torch.cat([t(ch.action_logits), ninf(C)], 1))
+            val = torch.where(is_dec, t(dec.afterstate_value), t(ch.value))
+            reward = torch.where(is_dec, torch.zeros_like(val), t(ch.reward))
+            discount = torch.where(is_dec, torch.ones_like(val), t(ch.discount))
+            new_emb = torch.cat([t(new_st), t(new_af), (~is_dec).to(f32)[:, None]], 1)
+            return reward, discount, p_logits, val, new_emb
+
+        action, weights, _ = engine.search_with_callback(
+            rng_key, root2, step, invalid_actions=invalid, noise=noise, policy=_lib.POLICY_MUZERO,
+            num_simulations=num_simulations, temperature=kwargs.get("temperature", 1.0),
+            max_depth=kwargs.get("max_depth"),
+            qtransform=resolve_qtransform(kwargs.get("qtransform", _lib.QT_PARENT_AND_SIBLINGS)),
+            dirichlet_fraction=kwargs.get("dirichlet_fraction", 0.25),
+            dirichlet_alpha=kwargs.get("dirichlet_alpha", 0.3), pb_c_init=kwargs.get("pb_c_init", 1.25),
+            pb_c_base=kwargs.get("pb_c_base", 19652), engine=_lib.ENGINE_STEPWISE, want_tree=True,
+            num_decision_actions=A)
+        return PolicyOutput(action=action, action_weights=weights[:, :A].contiguous(), search_tree=engine)

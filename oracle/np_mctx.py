@@ -526,8 +526,10 @@ class StochasticModel:
     def recurrent_inference(self, action, emb):
         B = emb.shape[0]
         state, after, is_dec = emb[:, :self.Es], emb[:, self.Es:self.Es + self.Ea], emb[:, -1] != 0
-        chance_logits, after_value, new_after = self.decision_fn(action, state)
-        act_logits, value, reward, discount, new_state = self.chance_fn(action - self.A, after)
+        # mctx hands both functions the raw pseudo-action and discards one result; the index a row does not use is
+        # clamped into range here (XLA's gather clamps out-of-range indices silently)
+        chance_logits, after_value, new_after = self.decision_fn(np.minimum(action, self.A - 1), state)
+        act_logits, value, reward, discount, new_state = self.chance_fn(np.maximum(action - self.A, 0), after)
         ninf = lambda n: np.full((B, n), -np.inf, F32)  # noqa: E731
         logits = np.where(is_dec[:, None], np.concatenate([ninf(self.A), chance_logits], 1),
                           np.concatenate([act_logits, ninf(self.C)], 1)).astype(F32)

@@ -105,3 +105,46 @@ def test_puct_pins():
     top2 = np.sort(np.where(legal, z["scores"], -np.inf), axis=-1)[:, -2:]
     clear = (top2[:, 1] - top2[:, 0]) > 1e-5                          # skip float32-level near-ties
     assert clear.mean() > 0.95 and np.array_equal(ours[clear], z["actions"][clear])
+
+
+def test_stochastic_restatement_invariants():
+    """oracle.np_mctx.stochastic_muzero_policy (mctx.stochastic_muzero_policy, muax/policy.py:50-67): decision and
+    chance nodes alternate by depth, chance nodes expand chance slots only, the visit summary covers the decision
+    actions, and the walk is reproducible from the key."""
+    from oracle import np_mctx
+    rng = np.random.default_rng(5)
+    B, A, C, NS, T = 12, 3, 4, 25, 53
+    tab_cl, tab_av = rng.standard_normal((T, C)).astype(np.float32), rng.standard_normal(T).astype(np.float32)
+    tab_al, tab_v, tab_r = (rng.standard_normal((T, A)).astype(np.float32), rng.standard_normal(T).astype(np.float32),
+                            rng.standard_normal(T).astype(np.float32))
+
+    def dec(action, state):
+        idx = (state[:, 0].astype(np.int64) * 7 + action.astype(np.int64) * 3 + 1) % T
+        return tab_cl[idx], tab_av[idx], idx.astype(np.float32)[:, None]
+
+    def ch(outcome, after):
+        idx = (after[:, 0].astype(np.int64) * 11 + outcome.astype(np.int64) * 5 + 2) % T
+        return tab_al[idx], tab_v[idx], tab_r[idx], np.full(idx.shape, 0.97, np.float32), idx.astype(np.float32)[:, None]
+
+    model = np_mctx.StochasticModel(np_mctx.ExactMath(), dec, ch, A, C, 1, 1)
+    root = (rng.standard_normal((B, A)).astype(np.float32), rng.standard_normal(B).astype(np.float32),
+            rng.integers(0, T, (B, 1)).astype(np.float32))
+    noise = rng.dirichlet([0.3] * A, B).astype(np.float32)
+    key = np.array([0, 9], np.uint32)
+    out = np_mctx.stochastic_muzero_policy(model, key, root, NS, dirichlet_noise=noise)
+    again = np_mctx.stochastic_muzero_policy(model, key, root, NS, dirichlet_noise=noise)
+    t = out["tree"]
+    assert np.array_equal(out["action"], again["action"]) and np.array_equal(t.children_visits, again["tree"].children_visits)
+    assert (t.node_visits[:, 0] == NS + 1).all() and (t.children_visits[:, 0, :A].sum(-1) == NS).all()
+    assert np.allclose(out["action_weights"].sum(-1), 1.0, atol=1e-6) and out["action_weights"].shape == (B, A)
+    is_dec = t.embeddings[:, :, -1] != 0
+    assert not ((t.children_index[:, :, A:] >= 0).any(-1) & is_dec).any()      # decision nodes expand actions
+    assert not ((t.children_index[:, :, :A] >= 0).any(-1) & ~is_dec).any()     # chance nodes expand outcomes
+    for b in range(B):
+        for n in range(1, NS + 1):
+            assert is_dec[b, n] != is_dec[b, t.parents[b, n]]
+    # afterstate edges carry reward 0 and discount 1
+    p, a = np.nonzero(t.children_index[0] >= 0)
+    dec_edges = is_dec[0, p]
+    assert (t.children_rewards[0, p[dec_edges], a[dec_edges]] == 0).all()
+    assert (t.children_discounts[0, p[dec_edges], a[dec_edges]] == 1).all()

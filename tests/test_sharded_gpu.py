@@ -61,6 +61,9 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.synchronize()
     res["async"] = [[t.cpu().numpy() for t in o] for o in outs]
     res["async_exchange"] = sh.exchange
+    # the end-to-end host path: NumPy rows in, everybody's results out (search + all-gather + one D2H)
+    obs_local_np = obs[rank * n:(rank + 1) * n]
+    res["host"] = [list(sh.act_host(np.array([7, step], np.uint32), obs_local_np, num_simulations=NS)) for step in range(5)]
     if rank == 0:
         full = engine(GB)
         ref = []
@@ -68,8 +71,9 @@ def _worker(rank, world, port, out_dir):
             a, w, v = full.search(np.array([7, step], np.uint32), obs=torch.from_numpy(obs).cuda(), num_simulations=NS)
             torch.cuda.synchronize()
             ref.append([t.cpu().numpy() for t in (a, w, v)])
-        ok = all(np.array_equal(x, y) and np.array_equal(x, z) and np.array_equal(x, u)
-                 for p, q, r, s in zip(res["peer"], res["nccl"], ref, res["async"]) for x, y, z, u in zip(p, q, r, s))
+        ok = all(np.array_equal(x, y) and np.array_equal(x, z) and np.array_equal(x, u) and np.array_equal(x, h)
+                 for p, q, r, s, hh in zip(res["peer"], res["nccl"], ref, res["async"], res["host"])
+                 for x, y, z, u, h in zip(p, q, r, s, hh))
         with open(os.path.join(out_dir, "result.txt"), "w") as f:
             f.write(f"{int(ok)}|{res['peer_exchange']}|{res['nccl_exchange']}|{res['async_exchange']}")
     dist.barrier()
