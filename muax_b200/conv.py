@@ -45,6 +45,7 @@ class ResNetRepresentation(nn.Module):
             n = self.torso(torch.zeros(1, frame_channels, height, width)).numel()
         self.project = nn.Linear(n, embedding_dim)
         self.embedding_dim = embedding_dim
+        self._torso16 = None  # bf16 copy of the torso, made on first use (throughput mode); stale after a weight update
 
     supports_bf16 = True  # MuZero._plan passes bf16=True in the throughput mode (precision="bf16")
 
@@ -53,8 +54,15 @@ class ResNetRepresentation(nn.Module):
         """uint8 frames stay uint8 until they are on the device (a quarter of the float32 H2D bytes); bf16=True runs
         the convolutions under autocast (tensor cores; the normalisations stay fp32)."""
         x = obs.permute(0, 3, 1, 2).to(torch.float32, memory_format=torch.channels_last) / 255.0
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(bf16) and x.is_cuda):
-            x = self.torso(x).to(torch.float32)
+        if bf16 and x.is_cuda:
+            # the torso is bandwidth-bound (24 convolutions + 24 normalisations over 42 x 42 x 32 activations): a bf16
+            # copy of its weights and bf16 activations halve the bytes (statistics are still accumulated in fp32)
+            if self._torso16 is None:
+                import copy
+                self._torso16 = copy.deepcopy(self.torso).to(torch.bfloat16)
+            x = self._torso16(x.to(torch.bfloat16)).to(torch.float32)
+        else:
+            x = self.torso(x)
         # min_max_normalize2d (muax/nn.py:48-56): per sample and channel over the spatial positions
         lo, hi = x.amin(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)
         scale = hi - lo

@@ -44,6 +44,10 @@ int treewarp_batched_begin(TreeWarpState& st, ResidentState& rs, const Tree& tre
 int treewarp_batched_select(TreeWarpState& st, int sim, cudaStream_t stream, int64_t* launches, std::string* err);
 int treewarp_batched_backup(TreeWarpState& st, const float* reward, const float* value, const float* logits,
                             const float* next_emb, cudaStream_t stream, int64_t* launches, std::string* err);
+// backup of simulation sim - 1 + selection of simulation sim in one launch (same lanes, records hot in L1)
+int treewarp_batched_backup_select(TreeWarpState& st, int sim, const float* reward, const float* value,
+                                   const float* logits, const float* next_emb, cudaStream_t stream, int64_t* launches,
+                                   std::string* err);
 int treewarp_batched_finish(TreeWarpState& st, int32_t* action_out, float* weights_out, cudaStream_t stream,
                             int64_t* launches, std::string* err);
 void treewarp_destroy(TreeWarpState& st);

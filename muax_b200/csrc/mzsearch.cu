@@ -597,13 +597,21 @@ static int search_tc(mz_handle* h, const float* obs, const float* root_logits, c
   // tree embeddings in bf16 (what the tensor core reads): the recurrent kernel gathers and stores them itself
   const bool clear16 = h->params.max_depth > 0 || NS + 1 < h->N;
   if (recurrent_tc_tree_begin(h->rtc, h->net, B, h->N, root_emb, clear16, stream, &h->launches, &err)) return fail(err);
+  // per simulation two launches: [backup of the previous simulation + selection] -> tcgen05 recurrent kernel
+  static const bool split = getenv("MZ_TC_SPLIT_BACKUP") != nullptr && atoi(getenv("MZ_TC_SPLIT_BACKUP")) != 0;  // A/B
   for (int sim = 0; sim < NS; ++sim) {
-    if (treewarp_batched_select(h->treewarp, sim, stream, &h->launches, &err)) return fail(err);
+    if (sim == 0 || split) {
+      if (treewarp_batched_select(h->treewarp, sim, stream, &h->launches, &err)) return fail(err);
+    } else if (treewarp_batched_backup_select(h->treewarp, sim, h->rec_reward, h->rec_value, h->rec_logits, nullptr,
+                                              stream, &h->launches, &err)) {
+      return fail(err);
+    }
     if (recurrent_tc_tree_launch(h->rtc, h->net, B, h->N, h->sel5, h->sel5 + B, h->sel5 + 2 * B, h->rec_reward,
                                  h->rec_value, h->rec_logits, stream, &h->launches, &err))
       return fail(err);
-    if (treewarp_batched_backup(h->treewarp, h->rec_reward, h->rec_value, h->rec_logits, nullptr, stream,
-                                &h->launches, &err))
+    if ((split || sim == NS - 1) &&
+        treewarp_batched_backup(h->treewarp, h->rec_reward, h->rec_value, h->rec_logits, nullptr, stream, &h->launches,
+                                &err))
       return fail(err);
   }
   h->tree16 = true;
