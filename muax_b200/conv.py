@@ -6,6 +6,10 @@ muax/nn.py:118-149 with LayerNorm over (H, W, C)) runs ONCE per act, at the root
 is the flat-embedding Dynamic / Prediction path of the CUDA engines.  So the torso is a plain torch / cuDNN module
 (library code: no kernel claim) whose output — flattened, projected to `embedding_dim`, min-max normalised like
 `Representation` (muax/nn.py:59-70) — is handed to the search as `root = (None, None, embedding)`.
+
+`ResNetTorso` / `ResNetPrediction` / `ResNetDynamic` are the reference's all-conv network (muax/nn.py:313-395) as torch
+modules: with them Prediction and Dynamic stay torch callables inside the simulation loop and the search runs through
+the library's callback mode (tree kernels native, nets in torch): `create_resnet_muzero_network`.
 """
 import torch
 from torch import nn
@@ -71,3 +75,89 @@ class ResNetRepresentation(nn.Module):
         lo, hi = s.amin(dim=1, keepdim=True), s.amax(dim=1, keepdim=True)  # min_max_normalize (muax/nn.py:37-44)
         scale = hi - lo
         return ((s - lo) / torch.where(scale < 1e-5, scale + 1e-5, scale)).contiguous()
+
+
+def _min_max_normalize2d(x):
+    """muax/nn.py:48-56 on NCHW tensors: per sample and channel over the spatial positions."""
+    lo, hi = x.amin(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)
+    scale = hi - lo
+    return (x - lo) / torch.where(scale < 1e-5, scale + 1e-5, scale)
+
+
+class ResNetTorso(nn.Module):
+    """The reference's `ResNetRepresentation` as is (muax/nn.py:313-331): frames [B, H, W, C] -> the spatial embedding,
+    returned FLAT in NHWC order ([B, h * w * c], what `hk.Flatten` would give) so that it can live in the tree."""
+
+    def __init__(self, input_channels=32, frame_channels=4, height=84, width=84):
+        super().__init__()
+        self.torso = ResNetRepresentation(8, input_channels, frame_channels, height, width).torso
+        with torch.no_grad():
+            c, h, w = self.torso(torch.zeros(1, frame_channels, height, width)).shape[1:]
+        self.shape = (int(h), int(w), int(c))  # NHWC shape of one embedding
+
+    @torch.no_grad()
+    def forward(self, obs):
+        x = obs.permute(0, 3, 1, 2).to(torch.float32, memory_format=torch.channels_last) / 255.0
+        x = _min_max_normalize2d(self.torso(x))
+        return x.permute(0, 2, 3, 1).reshape(x.shape[0], -1).contiguous()
+
+
+def _head(cin, channels, n_convs, spatial, out_dim):
+    layers, c = [], cin
+    for _ in range(n_convs):
+        layers += [nn.Conv2d(c, channels, 1, bias=False), nn.ReLU()]
+        c = channels
+    return nn.Sequential(*layers, nn.Flatten(), nn.Linear(channels * spatial, channels), nn.ReLU(),
+                         nn.Linear(channels, out_dim))
+
+
+class ResNetPrediction(nn.Module):
+    """muax/nn.py:334-361: 1x1-conv value head (two convs) and policy head (one conv) over the spatial embedding."""
+
+    def __init__(self, shape, num_actions, full_support_size, output_channels=16):
+        super().__init__()
+        self.shape = tuple(shape)
+        h, w, c = self.shape
+        self.v_func = _head(c, output_channels, 2, h * w, full_support_size)
+        self.pi_func = _head(c, output_channels, 1, h * w, num_actions)
+
+    @torch.no_grad()
+    def forward(self, s):
+        h, w, c = self.shape
+        x = s.reshape(-1, h, w, c).permute(0, 3, 1, 2)
+        return self.v_func(x), self.pi_func(x)
+
+
+class ResNetDynamic(nn.Module):
+    """muax/nn.py:364-395: the action as a constant plane a / num_actions appended to the embedding; reward head of
+    two 1x1 convs + two linears; next state = 1x1 conv + 8 residual blocks, min-max normalised per channel."""
+
+    def __init__(self, shape, num_actions, full_support_size, output_channels=64):
+        super().__init__()
+        self.shape, self.num_actions = tuple(shape), num_actions
+        h, w, c = self.shape
+        self.r_func = _head(c + 1, output_channels, 2, h * w, full_support_size)
+        self.ns_func = nn.Sequential(nn.Conv2d(c + 1, output_channels, 1, bias=False), nn.ReLU(),
+                                     *[_ResBlockV1(output_channels, output_channels) for _ in range(8)])
+        if output_channels != c:
+            raise ValueError("the next state must have the embedding's channel count (reference: 64)")
+
+    @torch.no_grad()
+    def forward(self, s, a):
+        h, w, c = self.shape
+        x = s.reshape(-1, h, w, c).permute(0, 3, 1, 2)
+        plane = (a.to(torch.float32) / self.num_actions).view(-1, 1, 1, 1).expand(-1, 1, h, w)
+        sa = torch.cat([x, plane], dim=1)
+        ns = _min_max_normalize2d(self.ns_func(sa))
+        return self.r_func(sa), ns.permute(0, 2, 3, 1).reshape(ns.shape[0], -1).contiguous()
+
+
+def create_resnet_muzero_network(num_actions, full_support_size, input_channels=32, frame_channels=4, height=84,
+                                 width=84, device="cuda"):
+    """The reference's all-conv MuZero (`ResNetRepresentation` / `ResNetPrediction` / `ResNetDynamic`) as an
+    `MZNetwork` of torch callables: `muax_b200.MuZero(network, ...)` then searches through the callback mode."""
+    from .nn import MZNetwork
+    torso = ResNetTorso(input_channels, frame_channels, height, width).to(device).eval()
+    pred = ResNetPrediction(torso.shape, num_actions, full_support_size).to(device).eval()
+    dyn = ResNetDynamic(torso.shape, num_actions, full_support_size, output_channels=torso.shape[2]).to(device).eval()
+    return MZNetwork(torso, pred, dyn)

@@ -7,6 +7,8 @@ timeout 300 python bench.py 2>&1 | tail -1 > $O/bench_n1.json
 run --steps 20 --warmup 3 > $O/bench_weak.json
 run --steps 20 --warmup 3 --scaling strong > $O/bench_strong.json
 run --steps 5 --warmup 3 --workload atari_conv_e256_b1024_sim50 > $O/bench_conv_weak.json
+run --steps 5 --warmup 3 --workload atari_conv_e256_b1024_sim50 --precision bf16 > $O/bench_conv_weak_bf16.json
+run --steps 5 --warmup 3 --workload atari_mlp_e256_b1024_sim50 --precision bf16 > $O/bench_atari_weak_bf16.json
 run --impl reference --steps 3 --warmup 1 > $O/bench_reference.json
 python - <<PY
 import json,glob
