@@ -25,7 +25,7 @@ MZ_LIB_PATH=$PWD/muax_b200/libmzsearch_clk.so timeout 300 python bench.py --work
 MZ_LIB_PATH=$PWD/muax_b200/libmzsearch_clk.so timeout 300 python tools/bench_recurrent.py 2>&1 | grep -E "tc clk|us_per_call" > $O/tc_clk_micro.txt
 timeout 300 python tools/bench_recurrent.py > $O/recurrent_micro.txt 2>&1
 # memory checker on the throughput mode and the stochastic path (small cases)
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_tc.py tests/test_gpu_stochastic.py -m gpu -x -q -k "batched or stochastic_muzero or stays_close" > $O/memcheck.txt 2>&1; echo "memcheck rc=$?" >> $O/memcheck.txt
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_tc.py tests/test_gpu_stochastic.py -m gpu -x -q -k "batched or stochastic_muzero or stays_close" > $O/memcheck.txt 2>&1; echo "memcheck rc=$?" >> $O/memcheck.txt
 tail -5 $O/memcheck.txt
 cat $O/pytest_gpu.txt $O/smoke.txt
 python - <<PY
