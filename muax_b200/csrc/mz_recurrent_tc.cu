@@ -42,25 +42,36 @@ static int tc_stage_env() {  // MZ_TC_STAGE_KB: A/B knob; 0 = choose per program
   static const int v = getenv("MZ_TC_STAGE_KB") != nullptr ? std::max(8, std::min(64, atoi(getenv("MZ_TC_STAGE_KB")))) * 1024 : 0;
   return v;
 }  // weight ring depth: as many stages (2 .. 8) as shared memory has room for
-constexpr int kTcMaxSteps = 32;  // 4 heads x MZ_MAX_LAYERS
+constexpr int kTcMaxSteps = 48;  // 4 heads x MZ_MAX_LAYERS, plus the second halves of the wide hidden layers (pipelined programs)
 constexpr int kTcEpiWarps = 8;   // epilogue warps: warp w reads TMEM lanes 32 * (w % 4) .. + 31, column half w / 4
 constexpr int kTcEpiThreads = 32 * kTcEpiWarps;
-constexpr int kTcThreads = kTcEpiThreads + 64;  // + warp 8: MMA issuer, warp 9: TMA producer
+constexpr int kTcStoreWarps = 2;  // copy the new embedding rows out of the operand buffer into the bf16 tree
+constexpr int kTcThreads = kTcEpiThreads + 64 + 32 * kTcStoreWarps;  // + warp 8: MMA issuer, warp 9: TMA producer, then the store warps
 constexpr uint32_t kTcChunkPitch = kTcM * 16;   // bytes between the 16-byte k-chunks of the A operand
 
 enum { kEpiHidden = 0, kEpiNextState = 1, kEpiReward = 2, kEpiValue = 3, kEpiPolicy = 4 };
 enum { kBufA = 0, kBufH0 = 1, kBufH1 = 2 };
 
+// One step = one GEMM (a whole layer, or one half of the output columns of a wide hidden layer) + its epilogue.  The
+// steps of a program form a dataflow graph, not a chain: the MMA issuer, the weight producer and the epilogue warps
+// all walk the table in order, every step has its own pair of single-use mbarriers (accumulators complete / epilogue
+// done), and the issuer waits only for the ONE earlier epilogue (`dep`) that covers everything the step needs — the
+// buffer it reads was written, the accumulator columns it overwrites were drained.  Independent heads are interleaved
+// and wide layers cut in two column halves on alternate accumulator regions, so the tensor core works on one step
+// while the epilogue warps finish another.
 struct TcStep {
   int32_t a_buf, out_buf;  // A operand of the GEMM / buffer the epilogue writes (hidden and next-state steps)
   int32_t k16;             // K / 16 after padding
   int32_t kc;              // k values per weight chunk (multiple of 16): kc * npad * 2 bytes <= stage_bytes
-  int32_t n, npad;         // true and padded (multiple of 16) output width
+  int32_t n, npad;         // true and padded (multiple of 16) width of the step's output columns
   int32_t epi;
-  int32_t bias_sh;         // float offset of the layer's (zero-padded) bias in the shared-memory bias table
+  int32_t bias_sh;         // float offset of the step's (zero-padded) bias row in the shared-memory bias table
   int32_t minmax;          // kEpiNextState: min_max_normalize the row
+  int32_t acc_col;         // first accumulator column of the step in tensor memory
+  int32_t n_off;           // first output column of the layer this step computes (0 unless the layer is cut in two)
+  int32_t dep;             // the epilogue the step's MMAs wait for (-1: only the gathered input operand)
   int64_t b_off;           // bias offset (floats) in the raw fp32 blob
-  int64_t img_off;         // bf16-element offset of the layer's operand image
+  int64_t img_off;         // bf16-element offset of the step's operand image
 };
 
 struct TcArgs {
@@ -85,6 +96,7 @@ struct TcArgs {
   float *reward, *value, *logits, *next_emb;
   int32_t B, A, S, act_kind, out_dim;  // out_dim: width of next_emb rows (E)
   int32_t kx16;             // k16 of the input operand
+  int32_t ns_step;          // the step that ends in kEpiNextState (-1: none)
   int32_t bufA_bytes, bufH_bytes, bufH1_bytes, stage_bytes, n_stages, bias_floats, tmem_cols;  // bufH1_bytes = 0 unless a head has >= 3 layers
   // hidden activations in tensor memory instead of shared memory (the A operand of the next layer is then read from
   // TMEM: `tcgen05.mma [d], [a], b-desc`): bf16 pairs packed into 32-bit columns h_col[0] / h_col[1] .. of the allocation
@@ -314,9 +326,56 @@ __device__ __forceinline__ float tc_head_scalar(uint32_t trow, const float* bias
   return mz_inv_scaling(x / sum);
 }
 
+// Next-state epilogue, pass 1: min / max of columns [c0, c0 + W) of the row (+ bias); pass 2: normalise, store fp32 to
+// global (when asked) and bf16 into the A operand buffer.
+template <int W>
+__device__ __forceinline__ void tc_ns_minmax(uint32_t trow, int c0, const float* bias, int n, float& lo, float& hi) {
+  float v[W];
+  tc_ldw<W>(trow + (uint32_t)c0, v);
+  tc_add_bias<W>(v, bias, c0);
+  if (c0 + W <= n) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      lo = fminf(lo, v[i]);
+      hi = fmaxf(hi, v[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const bool in = c0 + i < n;
+      lo = fminf(lo, in ? v[i] : mz_inf());
+      hi = fmaxf(hi, in ? v[i] : -mz_inf());
+    }
+  }
+}
+template <int W>
+__device__ __forceinline__ void tc_ns_store(uint32_t trow, int c0, const float* bias, int n, float sub, float inv, float* dst,
+                                            bool dst_vec, uint32_t out_sh) {
+  float v[W];
+  tc_ldw<W>(trow + (uint32_t)c0, v);
+  tc_add_bias<W>(v, bias, c0);
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] = c0 + i < n ? (v[i] - sub) * inv : 0.0f;
+  if (dst != nullptr) {
+    if (dst_vec && c0 + W <= n) {
+#pragma unroll
+      for (int q = 0; q < W / 4; ++q)
+        __stcs(reinterpret_cast<float4*>(dst + c0) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i)
+        if (c0 + i < n) dst[c0 + i] = v[i];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < W / 8; ++q)
+    tc_sts16(out_sh + (uint32_t)(c0 / 8 + q) * kTcChunkPitch, tc_pack2(v[8 * q], v[8 * q + 1]),
+             tc_pack2(v[8 * q + 2], v[8 * q + 3]), tc_pack2(v[8 * q + 4], v[8 * q + 5]), tc_pack2(v[8 * q + 6], v[8 * q + 7]));
+}
+
 #ifdef MZ_TC_CLOCKS
 // timeline of CTA 0 (cycles since kernel start): [0] prologue done, [1] A operand written; per step s:
-// [4s+2] MMA issuer past bar_aready, [4s+3] last MMA of the step issued, [4s+4] epilogue past bar_acc, [4s+5] epilogue done
+// [4s+2] MMA issuer past its dependency, [4s+3] last MMA of the step issued, [4s+4] epilogue past bar_acc, [4s+5] epilogue done
 #define MZ_TCCLK(i) do { if (blockIdx.x == 0) tc_clk[(i)] = clock64() - tc_t0; } while (0)
 #else
 #define MZ_TCCLK(i) do { } while (0)
@@ -328,7 +387,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
   __shared__ long long tc_clk[4 * kTcMaxSteps + 8];
   const long long tc_t0 = clock64();
 #endif
-  __shared__ __align__(8) uint64_t bar_full[kTcMaxStages], bar_empty[kTcMaxStages], bar_acc, bar_aready;
+  // bar_acc[s]: the accumulators of step s are complete (tcgen05.commit); bar_done[s]: every epilogue thread is through
+  // step s; bar_in: the gathered input operand is in shared memory.  Each is used once per kernel (parity 0).
+  __shared__ __align__(8) uint64_t bar_full[kTcMaxStages], bar_empty[kTcMaxStages], bar_acc[kTcMaxSteps], bar_done[kTcMaxSteps],
+      bar_in;
   __shared__ uint32_t tmem_base_sh;
   // the step table, copied out of the kernel parameters: a dynamically indexed parameter read is a constant-cache
   // access of several hundred cycles (per field, per step and per weight chunk it cost ~700 cycles per layer on the MMA
@@ -336,7 +398,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
   __shared__ TcStep steps_sh[kTcMaxSteps];
   __shared__ float row_lo[2][kTcM], row_hi[2][kTcM];  // partial row min / max of the two column halves
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  asm volatile("griddepcontrol.launch_dependents;");  // the next kernel of the stream may begin its own prologue
   // dynamic shared memory: A operand (input | one-hot, later the next state) | hidden 0 | hidden 1 | weight ring | biases
   uint8_t* stages = tc_smem + a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes;
   float* bias_all = reinterpret_cast<float*>(stages + (size_t)a.n_stages * a.stage_bytes);
@@ -352,8 +413,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
-    mbar_init(&bar_acc, 1);
-    mbar_init(&bar_aready, kTcEpiThreads);
+    for (int i = 0; i < a.n_steps; ++i) {
+      mbar_init(&bar_acc[i], 1);
+      mbar_init(&bar_done[i], kTcEpiThreads);
+    }
+    mbar_init(&bar_in, kTcEpiThreads);
   }
   if (warp == 0) {  // one warp allocates the accumulator columns of tensor memory (and frees them at the end)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
@@ -403,6 +467,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
       uint32_t st = 0, round = 0;
       for (int s = 0; s < n_steps; ++s) {
         const int kpad = steps_sh[s].k16 * 16, npad = steps_sh[s].npad, kc0 = steps_sh[s].kc, a_buf = steps_sh[s].a_buf;
+        const int dep = steps_sh[s].dep;
+        const uint32_t d_tmem = tmem_base + (uint32_t)steps_sh[s].acc_col;
         const uint32_t idesc = tc_idesc(npad);
         const bool a_tmem = h_tmem && a_buf != kBufA;
         // operands advance by a constant per MMA: two 16-byte k-chunks of A (shared memory: descriptor address field in
@@ -410,7 +476,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
         uint64_t adesc = tc_smem_desc(buf_sh(a_buf), kTcChunkPitch, 128u);
         uint32_t a_col = tmem_base + (uint32_t)(a_buf == kBufH1 ? h_col1 : h_col0);
         const uint64_t b_step = (uint64_t)((2u * (uint32_t)npad * 16u) >> 4);
-        tc_mbar_wait(&bar_aready, (uint32_t)(s & 1));  // the A operand is in shared memory, the accumulators are drained
+        // the A operand is written, the accumulator columns are drained (epilogues finish in table order: one wait)
+        tc_mbar_wait(dep < 0 ? &bar_in : &bar_done[dep], 0u);
         tc_fence_after();
         MZ_TCCLK(4 * s + 2);
         uint32_t acc = 0;
@@ -420,8 +487,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
           uint64_t bdesc = tc_smem_desc(stages_sh + st * (uint32_t)stage_bytes, (uint32_t)npad * 16u, 128u);
           const int kc = min(kc0, kpad - k0);
           for (int j = 0; j < kc; j += 16) {
-            if (a_tmem) tc_mma_ts(tmem_base, a_col, bdesc, idesc, acc);
-            else tc_mma(tmem_base, adesc, bdesc, idesc, acc);
+            if (a_tmem) tc_mma_ts(d_tmem, a_col, bdesc, idesc, acc);
+            else tc_mma(d_tmem, adesc, bdesc, idesc, acc);
             acc = 1;
             adesc += (uint64_t)((2u * kTcChunkPitch) >> 4);
             a_col += 8;
@@ -430,11 +497,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
           tc_commit(&bar_empty[st]);  // frees the stage when these MMAs have read it
           if (++st == n_stages) { st = 0; ++round; }
         }
-        tc_commit(&bar_acc);  // the layer's accumulators are complete
+        tc_commit(&bar_acc[s]);  // the step's accumulators are complete
         MZ_TCCLK(4 * s + 3);
       }
     }
     __syncwarp();
+  } else if (warp >= kTcEpiWarps + 2) {
+    // ---- store warps: the new embedding rows, bf16, out of the A operand buffer (where the next-state epilogue has
+    // put them for Prediction) into the tree at [b][next[b]].  Lane = (row of an 8-row group, piece mod 4): one store
+    // instruction covers 8 rows x 64 contiguous bytes.  Off the epilogue warps' path: the copy used to hold them for
+    // ~6 k cycles per simulation (profiles/r02_recurrent_tc_timeline_*).  Nothing writes the buffer again.
+    if (a.out16 != nullptr && a.ns_step >= 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // `next` comes from the kernel before this one
+      const int sw = warp - (kTcEpiWarps + 2), rsub = lane >> 2, q = lane & 3, pieces = a.es / 8;
+      constexpr int kGroups = kTcM / 8 / kTcStoreWarps;  // 8-row groups per store warp
+      int nxt[kGroups];
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) nxt[g] = a.next[min(row0 + (sw * kGroups + g) * 8 + rsub, a.B - 1)];
+      tc_mbar_wait(&bar_done[a.ns_step], 0u);
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        const int rr = (sw * kGroups + g) * 8 + rsub;
+        if (row0 + rr >= a.B) continue;
+        __nv_bfloat16* dst16 = a.out16 + (size_t)(row0 + rr) * a.tree16_stride + (size_t)nxt[g] * a.es;
+        const uint32_t src_sh = buf_sh(kBufA) + (uint32_t)rr * 16u;
+        for (int c = q; c < pieces; c += 32) {  // eight pieces in flight
+          uint4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c + 4 * j < pieces)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
+                           : "r"(src_sh + (uint32_t)(c + 4 * j) * kTcChunkPitch));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c + 4 * j < pieces) __stcs(reinterpret_cast<uint4*>(dst16) + c + 4 * j, v[j]);
+        }
+      }
+    }
   } else {
     // ---- epilogue warps: thread = (row, column half)
     const int r = (warp & 3) * 32 + lane;  // 0..127 = TMEM lane
@@ -442,10 +541,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
     const int row = row0 + r;
     const bool live = row < a.B;
     const int rb = min(row, a.B - 1);
-    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t trow0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     {  // [input row, one-hot(action)] -> A operand (muax/nn.py:105-108); the two halves take alternate 16-byte chunks
       asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: everything above overlapped
                                                            // the kernel that selected (parent, action)
+      // Only now may the next kernel of the stream begin its prologue: the backup + select kernel that follows copies
+      // the tree records into shared memory before its own griddepcontrol.wait, so the kernel that wrote them (the
+      // one this kernel has just waited for) must be complete when it starts.
+      asm volatile("griddepcontrol.launch_dependents;");
+      if (tid == 0) MZ_TCCLK(4 * kTcMaxSteps + 2);  // released by griddepcontrol.wait
       if (a.in16 != nullptr) {
         // bf16 rows: a 16-byte piece of a row IS a k-chunk of the operand.  Lane = (row of an 8-row group, piece mod 4):
         // one load instruction covers 8 rows x 64 contiguous bytes (8 L1 wavefronts, against 32 for a lane-per-row
@@ -524,27 +628,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
       }
       }
       tc_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) reads
-      tc_mbar_arrive(&bar_aready);
+      tc_mbar_arrive(&bar_in);
       if (tid == 0) MZ_TCCLK(1);
     }
     for (int s = 0; s < n_steps; ++s) {
       const TcStep& st = steps_sh[s];
       const int n = st.n, npad = st.npad;
       const float* bias = bias_all + st.bias_sh;
-      // this thread's columns [cb, ce): the layer's columns are split in two halves of whole 32-column groups
+      const uint32_t trow = trow0 + (uint32_t)st.acc_col;  // this thread's row of the step's accumulators
+      // this thread's columns [cb, ce): the step's columns are split in two halves of whole 32-column groups
       const int split = min(npad, ((npad / 2 + 31) / 32) * 32);
       const int cb = half == 0 ? 0 : split, ce = half == 0 ? split : npad;
-      tc_mbar_wait(&bar_acc, (uint32_t)(s & 1));
+      tc_mbar_wait(&bar_acc[s], 0u);
       tc_fence_after();
       if (tid == 0) MZ_TCCLK(4 * s + 4);
       if (st.epi == kEpiHidden && h_tmem) {
-        const uint32_t h_taddr = trow + (uint32_t)(st.out_buf == kBufH1 ? h_col1 : h_col0);
+        const uint32_t h_taddr = trow0 + (uint32_t)((st.out_buf == kBufH1 ? h_col1 : h_col0) + st.n_off / 2);
         int c0 = cb;
         for (; c0 + 32 <= ce; c0 += 32) tc_epi_hidden_tmem<32>(trow, c0, bias, a.act_kind, h_taddr);
         for (; c0 < ce; c0 += 16) tc_epi_hidden_tmem<16>(trow, c0, bias, a.act_kind, h_taddr);
         tc_wait_st();
       } else if (st.epi == kEpiHidden) {
-        const uint32_t out_sh = buf_sh(st.out_buf) + (uint32_t)r * 16u;
+        const uint32_t out_sh = buf_sh(st.out_buf) + (uint32_t)r * 16u + (uint32_t)(st.n_off / 8) * kTcChunkPitch;
         int c0 = cb;
         for (; c0 + 32 <= ce; c0 += 32) tc_epi_hidden<32>(trow, c0, bias, a.act_kind, out_sh);
         for (; c0 < ce; c0 += 16) tc_epi_hidden<16>(trow, c0, bias, a.act_kind, out_sh);
@@ -553,17 +658,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
         // into the tree), bf16 into Prediction's A operand.  The two column halves of a row meet through shared memory.
         float lo = mz_inf(), hi = -mz_inf();
         if (st.minmax) {
-          for (int c0 = cb; c0 < ce; c0 += 16) {
-            float v[16];
-            tc_ld16(trow + (uint32_t)c0, v);
-            tc_add_bias<16>(v, bias, c0);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const bool in = c0 + i < n;
-              lo = fminf(lo, in ? v[i] : mz_inf());
-              hi = fmaxf(hi, in ? v[i] : -mz_inf());
-            }
-          }
+          int c0 = cb;
+          for (; c0 + 32 <= ce; c0 += 32) tc_ns_minmax<32>(trow, c0, bias, n, lo, hi);
+          for (; c0 < ce; c0 += 16) tc_ns_minmax<16>(trow, c0, bias, n, lo, hi);
           row_lo[half][r] = lo;
           row_hi[half][r] = hi;
           asm volatile("bar.sync 1, %0;" ::"r"(kTcEpiThreads) : "memory");  // the epilogue warps only
@@ -575,56 +672,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
         const float inv = st.minmax ? 1.0f / scale : 1.0f;
         const float sub = st.minmax ? lo : 0.0f;
         const uint32_t out_sh = buf_sh(st.out_buf) + (uint32_t)r * 16u;
-        float* dst = a.next_emb + (size_t)rb * a.out_dim;
+        float* dst = (live && a.next_emb != nullptr) ? a.next_emb + (size_t)rb * a.out_dim : nullptr;
         const bool dst_vec = (a.out_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(a.next_emb) & 15) == 0;
-        for (int c0 = cb; c0 < ce; c0 += 16) {
-          float v[16];
-          tc_ld16(trow + (uint32_t)c0, v);
-          tc_add_bias<16>(v, bias, c0);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = c0 + i < n ? (v[i] - sub) * inv : 0.0f;
-          if (live && a.next_emb != nullptr) {
-            if (dst_vec && c0 + 16 <= n) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                __stcs(reinterpret_cast<float4*>(dst + c0) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c0 + i < n) dst[c0 + i] = v[i];
-            }
-          }
-          tc_sts16(out_sh + (uint32_t)(c0 / 8) * kTcChunkPitch, tc_pack2(v[0], v[1]), tc_pack2(v[2], v[3]),
-                   tc_pack2(v[4], v[5]), tc_pack2(v[6], v[7]));
-          tc_sts16(out_sh + (uint32_t)(c0 / 8 + 1) * kTcChunkPitch, tc_pack2(v[8], v[9]), tc_pack2(v[10], v[11]),
-                   tc_pack2(v[12], v[13]), tc_pack2(v[14], v[15]));
+        {
+          int c0 = cb;
+          for (; c0 + 32 <= ce; c0 += 32) tc_ns_store<32>(trow, c0, bias, n, sub, inv, dst, dst_vec, out_sh);
+          for (; c0 < ce; c0 += 16) tc_ns_store<16>(trow, c0, bias, n, sub, inv, dst, dst_vec, out_sh);
         }
-        if (a.out16 != nullptr) {
-          // the new embedding, bf16, into the tree at [b][next[b]]: the rows now lie in the A operand buffer; the
-          // epilogue warps meet and copy them out with the gather's lane map (8 rows x 64 contiguous bytes per store).
-          // The Prediction layers read the same buffer meanwhile; nothing writes it again.
-          tc_fence_before();
-          tc_fence_proxy_async();
-          tc_mbar_arrive(&bar_aready);  // the next step's MMAs need not wait for the copy
-          asm volatile("bar.sync 1, %0;" ::"r"(kTcEpiThreads) : "memory");
-          const int rsub = lane >> 2, q = lane & 3, pieces = a.es / 8;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int rr = warp * 16 + 8 * h + rsub;
-            if (row0 + rr >= a.B) continue;
-            const int gb = row0 + rr;
-            __nv_bfloat16* dst16 = a.out16 + (size_t)gb * a.tree16_stride + (size_t)a.next[gb] * a.es;
-            const uint32_t src_sh = buf_sh(st.out_buf) + (uint32_t)rr * 16u;
-            for (int c = q; c < pieces; c += 4) {
-              uint4 v;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                           : "r"(src_sh + (uint32_t)c * kTcChunkPitch));
-              __stcs(reinterpret_cast<uint4*>(dst16) + c, v);
-            }
-          }
-          if (tid == 0) MZ_TCCLK(4 * s + 5);
-          continue;  // already arrived on bar_aready
-        }
+        // (the bf16 tree row is copied out of the operand buffer by the store warps, which wait for this step's barrier)
       } else if (st.epi == kEpiPolicy) {
         for (int c0 = cb; c0 < ce; c0 += 16) {
           float v[16];
@@ -667,8 +722,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
         if (live) (st.epi == kEpiReward ? a.reward : a.value)[row] = y;
       }
       tc_fence_before();       // this thread's TMEM loads are complete (tcgen05.wait::ld) and ordered before ...
-      tc_fence_proxy_async();  // ... and its shared-memory stores visible to ... the next step's MMAs
-      tc_mbar_arrive(&bar_aready);
+      tc_fence_proxy_async();  // ... and its shared-memory stores visible to ... the MMAs that wait for this step
+      tc_mbar_arrive(&bar_done[s]);
       if (tid == 0) MZ_TCCLK(4 * s + 5);
     }
   }
@@ -676,7 +731,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
   __syncthreads();
 #ifdef MZ_TC_CLOCKS
   if (blockIdx.x == 0 && tid == 0) {
-    printf("tc clk | prologue %lld A %lld |", tc_clk[0], tc_clk[1]);
+    printf("tc clk | prologue %lld released %lld A %lld |", tc_clk[0], tc_clk[4 * kTcMaxSteps + 2], tc_clk[1]);
     for (int s = 0; s < a.n_steps; ++s)
       printf(" s%d[k16=%d n=%d] mma_go %lld mma_issued %lld acc %lld epi_done %lld |", s, a.steps[s].k16, a.steps[s].npad,
              tc_clk[4 * s + 2], tc_clk[4 * s + 3], tc_clk[4 * s + 4], tc_clk[4 * s + 5]);
@@ -692,11 +747,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
 // W [K][N] fp32 row-major -> the bf16 operand image of the layer: chunks of kc k-values, inside a chunk
 // [k / 8][npad rows][8 k-values], zero padded to kpad x npad.
 __global__ void recurrent_tc_pack_kernel(const float* __restrict__ raw, __nv_bfloat16* __restrict__ img, int64_t w_off,
-                                         int K, int N, int kpad, int npad, int kc) {
+                                         int K, int N, int ldn, int kpad, int npad, int kc) {
   const int total = kpad * npad;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int k = idx / npad, n = idx - k * npad;
-    const float v = (k < K && n < N) ? raw[w_off + (int64_t)k * N + n] : 0.0f;
+    const float v = (k < K && n < N) ? raw[w_off + (int64_t)k * ldn + n] : 0.0f;
     const int c = k / kc, kk = k - c * kc;
     const size_t off = (size_t)c * npad * kc + ((size_t)(kk / 8) * npad + n) * 8 + (kk & 7);
     img[off] = __float2bfloat16_rn(v);
@@ -733,9 +788,9 @@ __global__ void recurrent_tc_export16_kernel(const __nv_bfloat16* __restrict__ e
 
 // ------------------------------------------------------------------------------------------ host side
 
-struct TcLayer {
-  int64_t w_off, img_off, b_off;
-  int K, N, kpad, npad, kc, bias_dst;  // bias_dst: float offset of the layer's padded bias row in the bias table
+struct TcLayer {  // one step's operand image: columns [n_off, n_off + N) of a layer of ldn output units (the offsets
+  int64_t w_off, img_off, b_off;  // already include n_off)
+  int K, N, ldn, kpad, npad, kc, bias_dst;  // bias_dst: float offset of the step's padded bias row in the bias table
 };
 struct TcProgram {
   TcArgs args{};
@@ -779,57 +834,139 @@ static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& h
     const mz_stack& s = *h.s;
     deepest = std::max(deepest, (int)s.n_layers);
     for (int l = 0; l < s.n_layers; ++l) {
-      const int K = l == 0 ? h.in : s.in_dim[l], N = s.out_dim[l];
-      const int kpad = round_up(K, 16), npad = round_up(N, 16);
+      const int npad = round_up(s.out_dim[l], 16);
       if (npad > 256) return fail("a layer is wider than 256 units");
-      if (n_steps >= kTcMaxSteps) return fail("too many layers");
       const bool last = l == s.n_layers - 1;
-      TcStep& t = a.steps[n_steps++];
-      t.a_buf = l == 0 ? kBufA : ((l - 1) & 1 ? kBufH1 : kBufH0);
-      t.out_buf = last ? kBufA : (l & 1 ? kBufH1 : kBufH0);
-      t.k16 = kpad / 16;
-      t.kc = 0;  // set below, once the stage size is known
-      t.n = N;
-      t.npad = npad;
-      t.epi = last ? h.final_epi : kEpiHidden;
-      t.minmax = last ? h.minmax : 0;
-      t.bias_sh = bias_floats;
-      bias_floats += npad;
-      t.b_off = s.b_off[l];
-      t.img_off = (int64_t)*img;
-      impl->layers.push_back(TcLayer{s.w_off[l], (int64_t)*img, s.b_off[l], K, N, kpad, npad, t.kc,
-                                     (int)(*bias_base + t.bias_sh)});
-      *img += (size_t)kpad * npad;
       max_npad = std::max(max_npad, npad);
       if (!last) max_hidden_pad = std::max(max_hidden_pad, npad);
       if (last && h.final_epi == kEpiNextState) bufA_k = std::max(bufA_k, npad);
     }
   }
-  a.n_steps = n_steps;
-  a.in_dim = in_dim;
-  a.kx16 = round_up(in_dim + (onehot_actions ? num_actions : 0), 16) / 16;
-  a.bufA_bytes = bufA_k / 8 * (int)kTcChunkPitch;
-  a.bufH_bytes = max_hidden_pad / 8 * (int)kTcChunkPitch;
-  a.bufH1_bytes = deepest >= 3 ? a.bufH_bytes : 0;
-  a.bias_floats = bias_floats;
-  int need_cols = max_npad;
-  a.h_tmem = 0;
+  // groups of heads that read the same contents of buffer A: the head that ends in kEpiNextState rewrites it, the
+  // heads after it read the new row
+  std::vector<std::vector<int>> groups(1);
+  for (size_t h = 0; h < heads.size(); ++h) {
+    groups.back().push_back((int)h);
+    if (heads[h].final_epi == kEpiNextState && h + 1 < heads.size()) groups.emplace_back();
+  }
+  size_t widest_group = 0;
+  for (const auto& g : groups) widest_group = std::max(widest_group, g.size());
   // default on (bit-identical results; 133 against 160 cycles per N = 256 MMA and 64 KB of shared memory back for the
   // weight ring); MZ_TC_TMEM_H=0 keeps the hidden activations in shared memory
   static const bool want_h_tmem = getenv("MZ_TC_TMEM_H") == nullptr || atoi(getenv("MZ_TC_TMEM_H")) != 0;
-  if (want_h_tmem && deepest >= 2) {
-    // hidden activations in tensor memory: 16 accumulator-aligned columns per 32 hidden units, after the accumulators
-    const int hcols = round_up(max_hidden_pad / 2, 16);
+  static const bool want_pipe = getenv("MZ_TC_PIPE") == nullptr || atoi(getenv("MZ_TC_PIPE")) != 0;
+  const int hcols = round_up(max_hidden_pad / 2, 16);  // 16 accumulator-aligned columns per 32 hidden units
+  // Pipelined program (heads of <= 2 layers, <= 2 heads per group): the heads of a group are interleaved layer by layer
+  // (head q keeps its hidden activations in tensor-memory buffer q), hidden layers wider than 128 are cut into two
+  // column halves, and the steps alternate between two accumulator regions of `rw` columns.
+  const int rw = max_npad > 128 ? 128 : round_up(max_npad, 32);
+  const bool pipe = want_pipe && want_h_tmem && deepest <= 2 && widest_group <= 2 && 2 * rw + 2 * hcols <= 512;
+  a.h_tmem = 0;
+  int need_cols = max_npad;
+  if (pipe) {
+    a.h_tmem = 1;
+    a.h_col[0] = 2 * rw;
+    a.h_col[1] = 2 * rw + hcols;
+    need_cols = 2 * rw + 2 * hcols;
+  } else if (want_h_tmem && deepest >= 2) {
+    // hidden activations in tensor memory, after the accumulators
     const int total = round_up(max_npad, 16) + hcols * (deepest >= 3 ? 2 : 1);
     if (total <= 512) {
       a.h_tmem = 1;
       a.h_col[0] = round_up(max_npad, 16);
       a.h_col[1] = a.h_col[0] + hcols;
       need_cols = total;
-      a.bufH_bytes = 0;
-      a.bufH1_bytes = 0;
     }
   }
+  // the step table, in issue order
+  struct Emit { int head, layer; };
+  std::vector<Emit> order;
+  for (const auto& g : groups) {
+    if (pipe) {
+      for (int l = 0; l < deepest; ++l)
+        for (int h : g)
+          if (l < heads[h].s->n_layers) order.push_back(Emit{h, l});
+    } else {
+      for (int h : g)
+        for (int l = 0; l < heads[h].s->n_layers; ++l) order.push_back(Emit{h, l});
+    }
+  }
+  int last_writer[3] = {-1, -1, -1};  // latest step whose epilogue writes buffer A / hidden 0 / hidden 1
+  int region_user[2] = {-1, -1};      // latest step whose accumulators live in the region (pipelined programs)
+  int next_region = 0;
+  for (const Emit& e : order) {
+    const TcHead& h = heads[e.head];
+    const mz_stack& s = *h.s;
+    const int l = e.layer;
+    int q = 0;  // position of the head inside its group
+    for (const auto& g : groups)
+      for (size_t i = 0; i < g.size(); ++i)
+        if (g[i] == e.head) q = (int)i;
+    const int K = l == 0 ? h.in : s.in_dim[l], N = s.out_dim[l];
+    const int kpad = round_up(K, 16), npad = round_up(N, 16);
+    const bool last = l == s.n_layers - 1;
+    const bool cut = pipe && !last && npad > 128;
+    const int first = cut ? round_up(npad / 2, 32) : npad;
+    for (int part = 0; part < (cut ? 2 : 1); ++part) {
+      if (n_steps >= kTcMaxSteps) return fail("too many layers");
+      const int n_off = part == 0 ? 0 : first, np = part == 0 ? first : npad - first;
+      TcStep& t = a.steps[n_steps];
+      if (pipe) {
+        t.a_buf = l == 0 ? kBufA : (q ? kBufH1 : kBufH0);
+        t.out_buf = last ? kBufA : (q ? kBufH1 : kBufH0);
+      } else {
+        t.a_buf = l == 0 ? kBufA : ((l - 1) & 1 ? kBufH1 : kBufH0);
+        t.out_buf = last ? kBufA : (l & 1 ? kBufH1 : kBufH0);
+      }
+      t.k16 = kpad / 16;
+      t.kc = 0;  // set below, once the stage size is known
+      t.n = std::max(0, std::min(N - n_off, np));
+      t.npad = np;
+      t.n_off = n_off;
+      t.epi = last ? h.final_epi : kEpiHidden;
+      t.minmax = last ? h.minmax : 0;
+      t.bias_sh = bias_floats;
+      bias_floats += np;
+      t.b_off = s.b_off[l] + n_off;
+      t.img_off = (int64_t)*img;
+      // what the step's MMAs must wait for: the epilogues that write its A operand and the epilogues that read the
+      // accumulator columns it overwrites.  Epilogues complete in table order, so the latest of them covers all.
+      int dep = last_writer[t.a_buf];
+      if (pipe) {
+        if (np > rw) {  // both regions
+          t.acc_col = 0;
+          dep = std::max(dep, std::max(region_user[0], region_user[1]));
+          region_user[0] = region_user[1] = n_steps;
+          next_region = 0;
+        } else {
+          const int reg = cut ? part : next_region;
+          t.acc_col = reg * rw;
+          dep = std::max(dep, region_user[reg]);
+          region_user[reg] = n_steps;
+          next_region = reg ^ 1;
+        }
+      } else {
+        t.acc_col = 0;
+        dep = n_steps - 1;
+      }
+      t.dep = dep;
+      if (t.epi == kEpiHidden || t.epi == kEpiNextState) last_writer[t.out_buf] = n_steps;
+      impl->layers.push_back(TcLayer{s.w_off[l] + n_off, (int64_t)*img, s.b_off[l] + n_off, K, t.n, N, kpad, np, t.kc,
+                                     (int)(*bias_base + t.bias_sh)});
+      *img += (size_t)kpad * np;
+      ++n_steps;
+    }
+  }
+  a.n_steps = n_steps;
+  a.ns_step = -1;
+  for (int i = 0; i < n_steps; ++i)
+    if (a.steps[i].epi == kEpiNextState) a.ns_step = i;
+  a.in_dim = in_dim;
+  a.kx16 = round_up(in_dim + (onehot_actions ? num_actions : 0), 16) / 16;
+  a.bufA_bytes = bufA_k / 8 * (int)kTcChunkPitch;
+  a.bufH_bytes = a.h_tmem ? 0 : max_hidden_pad / 8 * (int)kTcChunkPitch;
+  a.bufH1_bytes = (!a.h_tmem && deepest >= 3) ? a.bufH_bytes : 0;
+  a.bias_floats = bias_floats;
   int cols = 32;
   while (cols < need_cols) cols <<= 1;
   a.tmem_cols = cols;
@@ -849,6 +986,15 @@ static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& h
   }
   *bias_base += bias_floats;
   prog.ok = true;
+  if (getenv("MZ_TC_DUMP") != nullptr) {  // the step table, for reading next to an MZ_TC_CLOCKS timeline
+    fprintf(stderr, "tc program: %d steps, %s, tmem %d cols (hidden at %d / %d), %d stages of %d KB\n", n_steps,
+            pipe ? "pipelined" : "serial", a.tmem_cols, a.h_col[0], a.h_col[1], a.n_stages, a.stage_bytes / 1024);
+    for (int i = 0; i < n_steps; ++i) {
+      const TcStep& t = a.steps[i];
+      fprintf(stderr, "  s%d: A=buf%d k16=%d kc=%d cols [%d, +%d/%d) acc@%d epi=%d out=buf%d dep=%d\n", i, t.a_buf, t.k16, t.kc,
+              t.n_off, t.n, t.npad, t.acc_col, t.epi, t.out_buf, t.dep);
+    }
+  }
   return true;
 }
 
@@ -941,7 +1087,7 @@ int recurrent_tc_pack(RecurrentTcState& st, const Net& net, const float* raw_wei
   for (const TcLayer& L : impl->layers) {
     const int total = L.kpad * L.npad;
     recurrent_tc_pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(raw_weights_dev, impl->images + L.img_off, L.w_off,
-                                                                      L.K, L.N, L.kpad, L.npad, L.kc);
+                                                                      L.K, L.N, L.ldn, L.kpad, L.npad, L.kc);
     recurrent_tc_bias_kernel<<<1, 256, 0, stream>>>(raw_weights_dev, impl->bias_table, L.b_off, L.N, L.npad, L.bias_dst);
     *launches += 2;
   }
