@@ -39,7 +39,7 @@ constexpr int kTcStageBytes = 16384;  // unit of the weight ring's stage size (1
                                       // many k values (a multiple of 16) as fit a stage — the whole layer for narrow ones
 constexpr int kTcMaxStages = 8;
 static int tc_stage_env() {  // MZ_TC_STAGE_KB: A/B knob; 0 = choose per program (tc_build)
-  static const int v = getenv("MZ_TC_STAGE_KB") != nullptr ? std::max(8, std::min(64, atoi(getenv("MZ_TC_STAGE_KB")))) * 1024 : 0;
+  static const int v = getenv("MZ_TC_STAGE_KB") != nullptr ? std::max(8, std::min(96, atoi(getenv("MZ_TC_STAGE_KB")))) * 1024 : 0;
   return v;
 }  // weight ring depth: as many stages (2 .. 8) as shared memory has room for
 constexpr int kTcMaxSteps = 48;  // 4 heads x MZ_MAX_LAYERS, plus the second halves of the wide hidden layers (pipelined programs)
@@ -556,16 +556,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) recurrent_tc_kernel(const __gri
         // walk), one store 8 rows x 16 bytes of 4 adjacent chunks.
         const int rsub = lane >> 2, q = lane & 3;
         const int D = a.in_dim, kpad = a.kx16 * 16, full = D / 8, chunks = kpad / 8;
+        // both row groups of the thread together: their (parent, action) loads form one L2 round trip and the first
+        // round of row pieces of both (sixteen 16-byte loads) the second — one group after the other was four
+        const __nv_bfloat16* src2[2];
+        uint32_t dst2[2];
+        int action2[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int rr = warp * 16 + 8 * h + rsub;  // row of the tile
           const int gb = min(row0 + rr, a.B - 1);
           const int parent = a.parent != nullptr ? a.parent[gb] : 0;
-          const int action = a.action != nullptr ? a.action[gb] : -1;
-          const __nv_bfloat16* src = a.in16 + (size_t)gb * a.tree16_stride + (size_t)parent * a.es;
-          const uint32_t dst = buf_sh(kBufA) + (uint32_t)rr * 16u;
-          int c = q;
-          for (; c + 28 < full; c += 32) {  // eight pieces in flight
+          action2[h] = a.action != nullptr ? a.action[gb] : -1;
+          src2[h] = a.in16 + (size_t)gb * a.tree16_stride + (size_t)parent * a.es;
+          dst2[h] = buf_sh(kBufA) + (uint32_t)rr * 16u;
+        }
+        const bool round0 = q + 28 < full;
+        if (round0) {  // eight pieces per group in flight
+          uint4 v[2][8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[h][j] = __ldcs(reinterpret_cast<const uint4*>(src2[h]) + q + 4 * j);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              tc_sts16(dst2[h] + (uint32_t)(q + 4 * j) * kTcChunkPitch, v[h][j].x, v[h][j].y, v[h][j].z, v[h][j].w);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const __nv_bfloat16* src = src2[h];
+          const uint32_t dst = dst2[h];
+          const int action = action2[h];
+          int c = q + (round0 ? 32 : 0);
+          for (; c + 28 < full; c += 32) {
             uint4 v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __ldcs(reinterpret_cast<const uint4*>(src) + c + 4 * j);
@@ -972,10 +996,19 @@ static bool tc_build(TcImpl* impl, TcProgram& prog, const std::vector<TcHead>& h
   a.tmem_cols = cols;
   const size_t fixed = (size_t)a.bufA_bytes + a.bufH_bytes + a.bufH1_bytes + (size_t)bias_floats * 4 + 128;
   const size_t budget = (size_t)max_smem - 2048;
-  // stage size: 32 KB (four MMAs per wait / commit at N = 256; C5: 3.01 against 3.09 ms per act) when at least four such
-  // stages fit, else 16 KB
-  a.stage_bytes = tc_stage_env() != 0 ? tc_stage_env()
-                                      : (fixed + 4 * (size_t)(2 * kTcStageBytes) <= budget ? 2 * kTcStageBytes : kTcStageBytes);
+  // stage size: the largest of 64 / 32 / 16 KB of which two fit.  Every chunk costs the issuer a wait / fence / commit
+  // round (~330 cycles measured), so few large chunks beat many small ones even with a shallower ring — C5, one
+  // 128-column step of K = 288: 3.65 k cycles with 16 KB stages, 3.0 k with 32 KB, 2.65 k with 64 KB (2.45 / 2.29 /
+  // 2.23 ms per act)
+  a.stage_bytes = tc_stage_env();
+  if (a.stage_bytes == 0) {
+    a.stage_bytes = kTcStageBytes;
+    for (int cand = 4 * kTcStageBytes; cand > kTcStageBytes; cand /= 2)
+      if (fixed + 2 * (size_t)cand <= budget) {
+        a.stage_bytes = cand;
+        break;
+      }
+  }
   if (fixed + 2 * (size_t)a.stage_bytes > budget) return fail("operands do not fit shared memory");
   a.n_stages = (int)std::min<size_t>(kTcMaxStages, (budget - fixed) / a.stage_bytes);
   prog.smem = fixed + (size_t)a.n_stages * a.stage_bytes;

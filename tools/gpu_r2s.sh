@@ -1,0 +1,14 @@
+set -x
+O=gpurun_out/r2s; mkdir -p $O
+for kb in 16 32 64; do
+  MZ_TC_STAGE_KB=$kb timeout 120 python bench.py --workload atari_mlp_e256_b1024_sim50 --steps 5 --warmup 3 --precision bf16 2>&1 | tail -1 > $O/bf16_stage${kb}.json
+done
+MZ_TC_STAGE_KB=16 MZ_TC_DUMP=1 MZ_LIB_PATH=$PWD/muax_b200/libmzsearch_clk.so timeout 300 python bench.py --workload atari_mlp_e256_b1024_sim50 --steps 1 --warmup 3 --precision bf16 2>&1 | grep -E "tc clk|tc program" | tail -2 > $O/tc_clk_stage16.txt
+MZ_TC_STAGE_KB=64 MZ_TC_DUMP=1 MZ_LIB_PATH=$PWD/muax_b200/libmzsearch_clk.so timeout 300 python bench.py --workload atari_mlp_e256_b1024_sim50 --steps 1 --warmup 3 --precision bf16 2>&1 | grep -E "tc clk|tc program" | tail -2 > $O/tc_clk_stage64.txt
+python - <<PY
+import json,glob
+for f in sorted(glob.glob("$O/*.json")):
+    try:
+        d=json.load(open(f)); print(f.split('/')[-1], "ms %.3f kernel_ms %.3f value %.1fM"%(d["ms_per_step"], d.get("roofline",{}).get("kernel_ms",0), d["value"]/1e6))
+    except Exception as e: print(f, "ERR", open(f).read()[-600:])
+PY
