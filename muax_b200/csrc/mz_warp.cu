@@ -179,9 +179,15 @@ __global__ void __launch_bounds__(128) noise_table_kernel(SearchParams p, int B,
 }
 
 
+// MZ_WARP_CACHED (default 1): selection scores cached per (node, child) and refreshed by a lane-parallel backup (see
+// the simulation loop of warp_search_kernel); 0 = the round-1 loop (scores computed on the walk, serial backup) for A/B.
+#ifndef MZ_WARP_CACHED
+#define MZ_WARP_CACHED 1
+#endif
+
 template <int A, int E>
 struct L2Layout {  // float offsets inside one tree block (all 16-byte aligned)
-  int nodes, childs, raw, logits, emb, root, stride;
+  int nodes, childs, raw, logits, emb, root, scores, path, stride;
   __host__ __device__ explicit L2Layout(int N) {
     int o = 0;
     nodes = o; o += 4 * N;
@@ -190,6 +196,8 @@ struct L2Layout {  // float offsets inside one tree block (all 16-byte aligned)
     logits = o; o += round_up(N * A, 4);
     emb = o; o += round_up(N * E, 4);
     root = o; o += round_up(2 * A, 4);  // root_noise[A], root_invalid[A] (as floats 0/1)
+    scores = o; o += MZ_WARP_CACHED ? round_up(N * A, 4) : 0;  // selection scores without the tie-break noise
+    path = o; o += MZ_WARP_CACHED ? round_up(N, 4) : 0;        // (node << 8 | action) per level of the last walk
     while (o % 32 != 4) o += 4;
     stride = o;
   }
@@ -490,6 +498,42 @@ __device__ __forceinline__ void w_prediction(const float* wq, float* sc, int l, 
   __syncwarp();
 }
 
+// muzero_action_selection (A.5) with qtransform_by_parent_and_siblings (A.6) for ALL children of node n, by one lane:
+// score[a] = value_score + prior_score, i.e. what the walk adds the tie-break noise to.  The operations (and their
+// order per child) are those of the on-the-walk selection; min / max over the visited children are order-independent.
+// A node's scores change only when a backup passes through it or when it is (re)expanded.
+template <int A>
+__device__ __forceinline__ void w_node_scores(const float4* nodes, const float4* childs, float* tsc, int n, float gamma) {
+  const float4 nd = nodes[n];
+  float4 ch[A];
+#pragma unroll
+  for (int x = 0; x < A; ++x) ch[x] = childs[n * A + x];
+  float q[A], lo = nd.y, hi = nd.y;
+#pragma unroll
+  for (int x = 0; x < A; ++x) {
+    q[x] = MZ_ADD(ch[x].w, MZ_MUL(gamma, ch[x].z));
+    const float qn = (__float_as_uint(ch[x].x) & 0xFFFFu) != 0u ? q[x] : mz_nan();  // fminf / fmaxf drop the NaN
+    lo = fminf(lo, qn);
+    hi = fmaxf(hi, qn);
+  }
+  const float denom = fmaxf(MZ_SUB(hi, lo), 1e-8f);
+#pragma unroll
+  for (int x = 0; x < A; ++x) {
+    const int vis = (int)(__float_as_uint(ch[x].x) & 0xFFFFu);
+    const float vnum = MZ_SUB(vis > 0 ? q[x] : lo, lo);
+    const float pnum = MZ_MUL(nd.z, ch[x].y);
+    const float pden = (float)(vis + 1);  // in [1, 65536]
+    bool bad = false;
+    float vsv = w_div_nn(vnum, denom, false, bad);
+    float psv = w_div_nn(pnum, pden, true, bad);
+    if (bad) {
+      vsv = MZ_DIV(vnum, denom);
+      psv = MZ_DIV(pnum, pden);
+    }
+    tsc[n * A + x] = MZ_ADD(vsv, psv);
+  }
+}
+
 template <int A, int E, int H, int S, int G>
 __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWMaxWarps + kWMaxProducers))
     warp_search_kernel(const __grid_constant__ LaneArgs a) {
@@ -600,6 +644,10 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
   float* tlog = blk + L.logits;
   float* temb = blk + L.emb;
   float* troot = blk + L.root;
+#if MZ_WARP_CACHED
+  float* tsc = blk + L.scores;
+  uint32_t* tpath = reinterpret_cast<uint32_t*>(blk + L.path);
+#endif
   SearchParams p = a.p;
   p.batch_offset += b;
 
@@ -689,6 +737,9 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
     for (int e = 4; e < E; e += 4) *reinterpret_cast<float4*>(temb + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
     traw[0] = rv;
     nodes[0] = make_float4(__int_as_float(1), rv, pbc[1], __uint_as_float(0xFFFFFFFFu));
+#if MZ_WARP_CACHED
+    w_node_scores<A>(nodes, childs, tsc, 0, gamma);  // every lane of the tree: same values, same stores
+#endif
   }
   __syncwarp();
 
@@ -734,8 +785,24 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
       // simulate (A.3) with muzero_action_selection (A.5) + qtransform_by_parent_and_siblings (A.6)
       int node = 0;
       for (;;) {
+#if MZ_WARP_CACHED
+        // the level's scores were left by the backup that last changed this node (w_node_scores): one load + the noise
+        const float base = tsc[node * A + axs];
+        const uint32_t chx = __float_as_uint(childs[node * A + axs].x);
+        const float* nzp = nzrow + depth * A;
+        if (!(use_table && depth < a.K)) {
+          l2_noise_cold<A>(a.p.sim_keys != nullptr ? a.p.sim_keys[2 * sim] : a.ik.w[2 * sim],
+                           a.p.sim_keys != nullptr ? a.p.sim_keys[2 * sim + 1] : a.ik.w[2 * sim + 1],
+                           (uint32_t)p.global_batch, (uint32_t)p.batch_offset, p.prng_mode, depth,
+                           use_table ? a.K : -1, contp, slot);
+          nzp = slot + 2;
+        }
+        float s = MZ_ADD(base, nzp[axs]);
+        if (depth == 0 && my_root_invalid) s = -mz_inf();
+#else
         const float4 nd = nodes[node];
         const float4 ch = childs[node * A + axs];
+        const uint32_t chx = __float_as_uint(ch.x);
         const float* nzp = nzrow + depth * A;
         if (!(use_table && depth < a.K)) {
           l2_noise_cold<A>(a.p.sim_keys != nullptr ? a.p.sim_keys[2 * sim] : a.ik.w[2 * sim],
@@ -771,13 +838,14 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
         }
         float s = MZ_ADD(MZ_ADD(vsv, psv), nz);
         if (depth == 0 && my_root_invalid) s = -mz_inf();
+#endif
         float bestv = __shfl_sync(gmask, s, abase);
-        uint32_t cx = __shfl_sync(gmask, __float_as_uint(ch.x), abase);
+        uint32_t cx = __shfl_sync(gmask, chx, abase);
         int best = 0;
 #pragma unroll
         for (int j = 1; j < A; ++j) {
           const float sj = __shfl_sync(gmask, s, abase + j);
-          const uint32_t cj = __shfl_sync(gmask, __float_as_uint(ch.x), abase + j);
+          const uint32_t cj = __shfl_sync(gmask, chx, abase + j);
           const bool better = sj > bestv;
           bestv = better ? sj : bestv;
           best = better ? j : best;
@@ -785,6 +853,9 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
         }
         action = best;
         const uint32_t ci = cx >> 16;
+#if MZ_WARP_CACHED
+        tpath[depth] = ((uint32_t)node << 8) | (uint32_t)best;  // every lane of the tree stores the same word
+#endif
         ++depth;
         if (ci == kNoChild || depth >= max_depth) {
           next = ci == kNoChild ? sim + 1 : (int)ci;
@@ -859,6 +930,59 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
         c.w = reward;
         childs[parent * A + action] = c;
       }
+#if MZ_WARP_CACHED
+      // backward (A.3), lane-parallel over the levels of the path the walk recorded: level d (edge tpath[d]: node pn,
+      // action) belongs to lane d of the tree's lanes, kWG levels per round starting from the leaf.  The only chain is
+      // the discounted return G_d = r_d + gamma * G_(d+1): every lane runs it over the round's rewards (shared memory
+      // broadcasts) and keeps its own level's value.  The value an edge stores for its child is the node value the
+      // lane one level deeper has just computed (one shuffle).  A lane then refreshes the cached selection scores of
+      // its node — its record and one of its children changed, by this very lane — and the lane at pseudo-level
+      // `depth` those of the (re)expanded node.  Same operations per level as the serial loop, ~190 instructions per
+      // simulation instead of ~35 per level + the scoring on the walk's dependent chain.
+      {
+        float* sr = sc + W::sE;  // the round's edge rewards (the heads' scratch is free until the next simulation)
+        const int topmax = __reduce_max_sync(0xffffffffu, (depth / kWG) * kWG);  // the trees of a warp differ in depth
+        float G_in = value, cv_in = value;
+        for (int d0 = topmax; d0 >= 0; d0 -= kWG) {
+          const int d = d0 + l;
+          const bool valid = d < depth;
+          const uint32_t pa = tpath[min(d, depth - 1)];
+          const int pn = (int)(pa >> 8), e2 = pn * A + (int)(pa & 0xFFu);
+          float4 c = childs[e2];
+          const float4 pd = nodes[pn];
+          sr[l] = c.w;
+          __syncwarp();
+          const int cnt = min(kWG, depth - d0);  // levels of this tree in the round (<= 0: none)
+          const int cntmax = __reduce_max_sync(0xffffffffu, cnt);
+          float Gr = G_in, myG = G_in;
+          for (int e = cntmax - 1; e >= 0; --e) {
+            if (e < cnt) Gr = MZ_ADD(sr[e], MZ_MUL(gamma, Gr));
+            if (e == l) myG = Gr;
+          }
+          G_in = Gr;
+          const int ci = __float_as_int(pd.x);
+          const float count = (float)ci;
+          const float pnum = MZ_ADD(MZ_MUL(pd.y, count), myG), pden = MZ_ADD(count, 1.0f);
+          // pden = count + 1 with count in [1, 65535]: only the numerator (any sign) needs the range check
+          const uint32_t un = __float_as_uint(pnum) & 0x7fffffffu;
+          float pv = div_core(pnum, pden);
+          if (!(un == 0u || (un - 0x30800000u) < 0x1E800000u)) pv = MZ_DIV(pnum, pden);
+          float cv = __shfl_down_sync(0xffffffffu, pv, 1, kWG);  // the node one level deeper, after its update
+          if (l == kWG - 1) cv = cv_in;                           // ... computed in the round before
+          if (d == depth - 1) cv = value;                         // ... or the new node
+          if (valid) {
+            nodes[pn] = make_float4(__int_as_float(ci + 1), pv, pbc[min(ci + 1, NS + 1)], pd.w);
+            c.x = __uint_as_float(__float_as_uint(c.x) + 1u);
+            c.z = cv;
+            childs[e2] = c;
+          }
+          cv_in = __shfl_sync(0xffffffffu, pv, 0, kWG);
+          if (d <= depth) w_node_scores<A>(nodes, childs, tsc, valid ? pn : next, gamma);
+          __syncwarp();
+        }
+      }
+    }
+#else
       // backward (A.3)
       int index = next;
       float G_ = value, child_value = value;
@@ -884,6 +1008,7 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
         index = pn;
       }
     }
+#endif
     __syncwarp();
   }
 
