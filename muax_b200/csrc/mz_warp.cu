@@ -400,7 +400,7 @@ __device__ __forceinline__ void w_minmax(float (&v)[N_], bool enabled) {
 // The same normalisation dealt out over the lanes of a tree: every lane finds min / max of the raw row (shared memory
 // at `raw`), lane k divides element k, the quotients meet in `tmp` and every lane reloads the row — one division per
 // lane instead of N_ (identical operations per element).
-template <int N_>
+template <int N_, int G_>
 __device__ __forceinline__ void w_minmax_dist(const float* raw, float* tmp, int l, bool enabled, float (&v)[N_]) {
   static_assert((N_ & (N_ - 1)) == 0, "power-of-two row");
   w_load<N_>(raw, v);
@@ -413,12 +413,15 @@ __device__ __forceinline__ void w_minmax_dist(const float* raw, float* tmp, int 
   }
   float scale = MZ_SUB(hi, lo);
   if (scale < 1e-5f) scale = MZ_ADD(scale, 1e-5f);
-  const int k = l & (N_ - 1);
-  const float num = MZ_SUB(raw[k], lo);
-  bool bad = !((__float_as_uint(scale) - 0x30800000u) < 0x1E800000u);
-  float qv = w_div_nn(num, scale, true, bad);
-  if (bad) qv = MZ_DIV(num, scale);
-  tmp[k] = qv;
+#pragma unroll
+  for (int k0 = 0; k0 < N_; k0 += G_) {  // one pass when the tree's lanes cover the row
+    const int k = (k0 + l) & (N_ - 1);
+    const float num = MZ_SUB(raw[k], lo);
+    bool bad = !((__float_as_uint(scale) - 0x30800000u) < 0x1E800000u);
+    float qv = w_div_nn(num, scale, true, bad);
+    if (bad) qv = MZ_DIV(num, scale);
+    tmp[k] = qv;
+  }
   __syncwarp();
   w_load<N_>(tmp, v);
 }
@@ -882,7 +885,7 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
       w_bias_act_store<U>(wq + W::D2 + H * 32, l, acc, false, 0, sc + W::sO1);
     }
     __syncwarp();
-    w_minmax_dist<E>(sc + W::sO1, sc + W::sE, l, net.dyn_minmax != 0, x);
+    w_minmax_dist<E, G>(sc + W::sO1, sc + W::sE, l, net.dyn_minmax != 0, x);
     w_prediction<A, E, H, S, G>(wq, sc, l, x, act_kind);
     const float hs = w_heads<A, E, H, S, G>(sc, l);
     const float reward = __shfl_sync(0xffffffffu, hs, lane & ~(kWG - 1));
@@ -1121,7 +1124,13 @@ static const std::vector<WarpVariant>& warp_variants() {
       MZ_WARP_VARIANT(2, 8, 16, 10),   // CartPole-v1 stock nets (README / BASELINE headline)
       MZ_WARP_VARIANT(4, 8, 16, 10),   // 4-action environments with the stock nets
       MZ_WARP_VARIANT(3, 8, 16, 10),
-      MZ_WARP_VARIANT(2, 8, 16, 5),
+      MZ_WARP_VARIANT(5, 8, 16, 10),   // up to 6 actions (one lane per action inside an 8-lane subgroup)
+      MZ_WARP_VARIANT(6, 8, 16, 10),
+      MZ_WARP_VARIANT(2, 8, 16, 5),    // support_size 5: 11-logit heads leave room for 16-wide embeddings
+      MZ_WARP_VARIANT(3, 8, 16, 5),
+      MZ_WARP_VARIANT(4, 8, 16, 5),
+      MZ_WARP_VARIANT(2, 16, 16, 5),
+      MZ_WARP_VARIANT(4, 16, 16, 5),
   };
   return v;
 }

@@ -191,6 +191,33 @@ def test_warp_engine_variants(c_oracle, monkeypatch, lanes, producers, A, S, B, 
         check_tree_invariants(got, NS)
 
 
+@pytest.mark.parametrize("lanes", ["8", "16"])
+@pytest.mark.parametrize("A,E,S,B,NS,max_depth", [(5, 8, 10, 70, 30, 0), (6, 8, 10, 45, 25, 4), (3, 8, 5, 50, 20, 0),
+                                                  (2, 16, 5, 130, 40, 0), (4, 16, 5, 66, 30, 0)])
+def test_warp_engine_wider_shapes(c_oracle, monkeypatch, lanes, A, E, S, B, NS, max_depth):
+    """The warp engine's other compiled shapes: 5 and 6 actions (an 8-lane action subgroup), support_size 5 with 8- and
+    16-wide embeddings — forced by name (engine = 8: the call fails if the shape is not compiled), bit-identical to
+    the C restatement, with invalid actions at the root and a depth limit."""
+    monkeypatch.setenv("MZ_WARP_LANES", lanes)
+    rng = np.random.default_rng(500 + 10 * A + E + S)
+    nets = make_nets(rng, 6, E, A, 2 * S + 1, bias_scale=0.05)
+    obs = rng.standard_normal((B, 6)).astype(np.float32)
+    invalid = (rng.random((B, A)) < 0.25).astype(np.uint8)
+    invalid[:, 1] = 0
+    key = np.array([11, 5000 + A + E], np.uint32)
+    cfg = dict(policy=0, qtransform=0, num_simulations=NS, support_size=S)
+    if max_depth:
+        cfg["max_depth"] = max_depth
+    want = c_oracle.search(nets, key, obs=obs, invalid=invalid, **cfg)
+    eng = _engine(nets, B, cfg, NS)
+    out = eng.search(key, obs=torch.from_numpy(obs).cuda(), invalid_actions=invalid, engine=8, **_search_kwargs(cfg))
+    got = _collect(eng, *out)
+    assert_same_search(got, want)
+    assert np.array_equal(got["sim_depth"], want["sim_depth"])
+    if not max_depth:
+        check_tree_invariants(got, NS)
+
+
 @pytest.mark.parametrize("lanes", ["8", "16", "32"])
 @pytest.mark.parametrize("policy,qt,A,E,hidden,S,B,NS,max_depth,K", [
     (0, 0, 4, 64, (16,), 10, 301, 60, 0, None),        # C3 stock shapes, ragged batch
