@@ -314,7 +314,18 @@ def run_ours(args, wl, name):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # The exchange is one 64 KB-per-rank all-gather per act, overlapped with the next act's search kernel, which
+        # occupies 147 of the 148 SMs (one CTA of 210 KB shared memory each).  With NCCL's default channel count its
+        # kernel's CTAs take SMs the next search kernel is waiting for (+19 us per act measured at N = 2); one channel
+        # is one CTA and fits the free SM.  A user's own setting wins.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("MZ_BENCH_NCCL_CHANNELS", "1"))
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
+        if os.environ.get("MZ_BENCH_NCCL_PRIO", "0") != "0":
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     B, GB = shard(args, wl, world)
     NS, A = wl["num_sim"], wl["A"]
     nets = make_nets(wl)
@@ -341,30 +352,41 @@ def run_ours(args, wl, name):
         return model.act_device(rng_key, obs_local, out=out, global_batch=global_batch, batch_offset=batch_offset,
                                 **act_kw, **kw)
 
-    sharded = ShardedSearch(search_fn, GB, A, writes_into_out=True)
+    # N > 1: the exchange is the NCCL all-gather of act t - 1 on a side stream, overlapped with act t.  MZ_BENCH_PEER=1
+    # selects the search kernel's own NVLink peer stores + completion flags instead (no NCCL, no barrier kernel;
+    # bit-identical, tests/test_sharded_gpu.py) — measured slower at the headline shapes on 2 x B200 (0.257 against
+    # 0.244 ms per step: the system-scope fences at the end of the kernel cost what the overlapped all-gather saves)
+    peer_mode = None if os.environ.get("MZ_BENCH_PEER", "0") != "0" else False
+    sharded = ShardedSearch(search_fn, GB, A, writes_into_out=True, peer_stores=peer_mode,
+                            engine=(lambda: model._engine_for(B, NS)) if not wl.get("conv") else None)
 
     def engine():
         return next(iter(model._engines.values()))[0]
 
     pending = []
+    # diagnostic only (default "full" = the contract): "nowait" leaves the exchange unawaited inside the timed steps,
+    # "none" does not launch it — to attribute the per-step cost of the exchange at N > 1
+    exchange_mode = os.environ.get("MZ_BENCH_EXCHANGE", "full")
+    exchange_lag = 2 if exchange_mode == "lag2" else 1
 
     def step_device(i):
         """act t on the main stream; the all-gather of act t - 1 starts at the same moment on the side stream and the
         step ends when both are done (N = 1: just the search)."""
         key = np.array([0, i], np.uint32)
-        prev = pending.pop() if pending else None
-        if prev is not None:
-            prev.launch()
+        if pending and exchange_mode != "none":
+            pending[-1].launch()          # the exchange of act t - 1 starts together with act t's search
         handle = sharded.act_async(key, obs_dev)
-        if prev is not None:
-            prev.wait()
+        if exchange_mode in ("full", "lag2") and len(pending) >= exchange_lag:
+            pending.pop(0).wait()         # ... and the step ends when the exchange of act t - lag is in
+        elif pending and exchange_mode not in ("full", "lag2"):
+            pending.pop(0)
         if world > 1:
             pending.append(handle)
         return handle
 
     def drain():
-        if pending:
-            h = pending.pop()
+        while pending:
+            h = pending.pop(0)
             h.launch()
             h.wait()
 

@@ -169,6 +169,16 @@ int mz_search(mz_handle* h, const float* obs_dev, const float* root_logits_dev, 
  * reads after the stores (a cross-rank barrier after the kernel). */
 int mz_set_peer_outputs(mz_handle* h, int32_t n, const int64_t* byte_deltas);
 
+/* Completion flags for that exchange, so that no barrier kernel sits between two acts: flags_dev = W int32 words in
+ * this rank's (symmetric) gather buffer, one per source rank.  With flags set, the last CTA of the next mz_search's
+ * kernel — after every output store, local and peer, has been fenced system-wide — stores `step` at flags_dev[rank]
+ * and at the same word of every peer (flags_dev + rank, shifted by the byte_deltas of mz_set_peer_outputs).  Steps
+ * must increase.  flags_dev = NULL switches it off.  mz_peer_wait enqueues a one-CTA kernel on `stream` that returns
+ * when flags_dev[q] >= step for all q < world (every rank's rows of act `step` have arrived here); it gives up after
+ * a few seconds of polling instead of hanging the device. */
+int mz_set_peer_flags(mz_handle* h, int32_t* flags_dev, int32_t rank, int32_t step);
+int mz_peer_wait(mz_handle* h, const int32_t* flags_dev, int32_t world, int32_t step, void* stream);
+
 /* Same call with HOST buffers (what `MuZero.act` sees: numpy in, numpy out — model.py:160-174): stages
  * through mapped pinned memory (read / written in place by the kernels; copy-engine H2D for large observation
  * batches), searches and synchronises the stream. */

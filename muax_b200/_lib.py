@@ -21,7 +21,7 @@ FLAG_WANT_TREE = 1
 OK, ERR_RUNTIME, ERR_INVALID_ARGUMENT = 0, 1, 2
 
 EXPORTS = ("mz_last_error", "mz_default_args", "mz_create", "mz_destroy", "mz_set_weights", "mz_search",
-           "mz_search_host", "mz_set_peer_outputs", "mz_recurrent", "mz_begin", "mz_select", "mz_expand_backup", "mz_finish", "mz_get_tree",
+           "mz_search_host", "mz_set_peer_outputs", "mz_set_peer_flags", "mz_peer_wait", "mz_recurrent", "mz_begin", "mz_select", "mz_expand_backup", "mz_finish", "mz_get_tree",
            "mz_launch_count", "mz_last_kernel_ms", "mz_math_probe")
 
 
@@ -82,6 +82,8 @@ def load(build_if_missing=True):
     lib.mz_search.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(SearchArgs), vp, vp, vp, vp]
     lib.mz_search_host.argtypes = [vp, vp, vp, vp, ctypes.POINTER(SearchArgs), vp, vp, vp, vp]
     lib.mz_set_peer_outputs.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
+    lib.mz_set_peer_flags.argtypes = [vp, vp, i32, i32]
+    lib.mz_peer_wait.argtypes = [vp, vp, i32, i32, vp]
     lib.mz_recurrent.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.mz_begin.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.POINTER(SearchArgs), vp]
     lib.mz_select.argtypes = [vp, i32, vp, vp, vp]

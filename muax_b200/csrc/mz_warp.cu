@@ -81,6 +81,11 @@ struct LaneArgs {
   // the peer GPUs' gather buffers (NVLink peer stores; muax_b200/sharded.py)
   int32_t n_peers;
   int64_t peer_delta[7];
+  // completion flag of the sharded act (mz_set_peer_flags): the grid's last CTA, once every output store (local and
+  // peer) is fenced system-wide, stores flag_step at flag[flag_rank] here and at the same slot of every peer
+  int32_t* flag;
+  int32_t flag_rank, flag_step;
+  uint32_t* done_counter;  // CTAs of this launch that have finished (reset by the last one)
   SimKeys ik;  // simulate keys by value (p.sim_keys == nullptr), else p.sim_keys points at them in device memory
 };
 
@@ -546,6 +551,7 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
   static_assert(G == 8 || G == 16, "8 or 16 lanes per tree");
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t wbar;
+  __shared__ unsigned cta_done;  // search warps of this CTA whose outputs are stored
   const LaneNet& net = a.net;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int l = lane & (kWG - 1);
@@ -567,6 +573,7 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
 
   // ---- prologue: weights by one TMA bulk copy, pb_c table, tree init, re-layout of the 4 two-head matrices
   if (tid == 0) {
+    cta_done = 0u;
     for (int i = 0; i < kWRing; ++i) {
       mbar_init(&nz_full[i], 32);          // every lane of the producing warp arrives
       mbar_init(&nz_empty[i], (uint32_t)(32 * SW));  // every lane of every search warp arrives (releases its own reads)
@@ -1057,6 +1064,28 @@ __global__ void __launch_bounds__(G == 8 ? 32 * (8 + kWMaxProducers) : 32 * (kWM
     }
   }
 
+    // ---- completion flag of the sharded act: the exchange is this kernel's own peer stores, so "everybody's rows have
+    // arrived" is a flag per source rank in every rank's gather buffer, set by the LAST CTA of the source's kernel.
+    // Every lane fences its output stores system-wide, the warp's lane 0 counts the warp in, the CTA's last warp counts
+    // the CTA in, the grid's last CTA publishes (the fence-then-count pattern of a last-block reduction, at system scope).
+    if (a.flag != nullptr) {
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0 && atomicAdd(&cta_done, 1u) == (unsigned)(SW - 1)) {
+        __threadfence();
+        if (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) {
+          atomicExch(a.done_counter, 0u);
+          __threadfence_system();
+          int32_t* mine = a.flag + a.flag_rank;
+          asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(mine), "r"(a.flag_step) : "memory");
+          for (int q = 0; q < a.n_peers; ++q)
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(reinterpret_cast<char*>(mine) + a.peer_delta[q]),
+                         "r"(a.flag_step)
+                         : "memory");
+        }
+      }
+    }
+
     // ---- dump: every warp unpacks its own trees into the mctx SoA arrays as soon as it is done (no CTA barrier:
     // the act ends with its slowest warp, the others have written their trees by then)
     if (a.dump_tree) {
@@ -1204,7 +1233,9 @@ int warp_init(WarpState& st, const Net& net, int device, std::string* err) {
     delete impl;
     return 0;
   }
-  if (cudaMalloc((void**)&st.packed, (size_t)round_up(off, 4) * 4 + 16) != cudaSuccess) {
+  if (cudaMalloc((void**)&st.packed, (size_t)round_up(off, 4) * 4 + 16) != cudaSuccess ||
+      cudaMalloc((void**)&st.done_counter, 16) != cudaSuccess || cudaMemset(st.done_counter, 0, 16) != cudaSuccess) {
+    cudaGetLastError();
     delete impl;
     *err = "warp engine: cudaMalloc(packed weights) failed";
     return 1;
@@ -1220,6 +1251,8 @@ int warp_init(WarpState& st, const Net& net, int device, std::string* err) {
 
 void warp_destroy(WarpState& st) {
   if (st.packed) cudaFree(st.packed);
+  if (st.done_counter) cudaFree(st.done_counter);
+  st.done_counter = nullptr;
   if (st.noise_table) cudaFree(st.noise_table);
   if (st.cont_keys) cudaFree(st.cont_keys);
   st.packed = nullptr;
@@ -1291,6 +1324,10 @@ int warp_launch(WarpState& st, const Tree& out, const SearchParams& p, const Sim
   a.N = N;
   a.n_peers = (int)std::min<size_t>(peers.size(), 7);
   for (int i = 0; i < a.n_peers; ++i) a.peer_delta[i] = peers[i];
+  a.flag = st.flag;
+  a.flag_rank = st.flag_rank;
+  a.flag_step = st.flag_step;
+  a.done_counter = st.done_counter;
   a.dump_tree = dump_tree ? 1 : 0;
   a.K = std::min(16, kGNoiseFloats / A);
   if (const char* k = getenv("MZ_GROUP_K")) a.K = std::max(0, std::min(a.K, atoi(k)));
@@ -1342,6 +1379,36 @@ int warp_launch(WarpState& st, const Tree& out, const SearchParams& p, const Sim
     return 1;
   }
   return 0;
+}
+
+// One thread per source rank spins (system-scope acquire loads) until the rank's flag reaches `step`.  Bounded: a flag
+// that never comes is a protocol bug or a dead peer, and must not hang the GPU.
+__global__ void peer_wait_kernel(const int32_t* flags, int world, int step, int32_t* timed_out) {
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  for (unsigned spin = 0;; ++spin) {
+    int32_t v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + q) : "memory");
+    if (v >= step) return;
+    if (spin > (1u << 24)) {  // ~ seconds
+      if (timed_out != nullptr) atomicExch(timed_out, 1);
+      return;
+    }
+    __nanosleep(200);
+  }
+}
+
+int warp_peer_wait(WarpState& st, const int32_t* flags, int world, int step, cudaStream_t stream, int64_t* launches) {
+  // same shared-memory carve-out as the search kernel it follows: a kernel with another preference makes the SMs
+  // reconfigure their L1 / shared memory split before it may start
+  static const bool once = [] {
+    cudaFuncSetAttribute(peer_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)once;
+  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, world, step, reinterpret_cast<int32_t*>(st.done_counter) + 1);
+  *launches += 1;
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace mz

@@ -20,6 +20,11 @@ struct WarpState {
   int force_warps = 0;  // MZ_WARP_WARPS: search warps per CTA
   int lanes = 16;       // MZ_WARP_LANES: lanes per tree (8 or 16)
   int producers = 2;    // MZ_WARP_PRODUCERS: noise-producer warps per CTA (0 = pre-pass kernel + table in HBM)
+  // sharded act with peer stores: completion flags (mz_set_peer_flags) and the launch's finished-CTA counter
+  // (done_counter[0]; done_counter[1] = a peer wait timed out)
+  int32_t* flag = nullptr;
+  int32_t flag_rank = 0, flag_step = 0;
+  uint32_t* done_counter = nullptr;
 };
 
 int warp_init(WarpState& st, const Net& net, int device, std::string* err);
@@ -28,6 +33,8 @@ int warp_pack(WarpState& st, const float* raw_weights, cudaStream_t stream, int6
 bool warp_supported(const WarpState& st, const SearchParams& p, int B);
 // inline_keys != null: the simulate keys travel in the kernel parameters (p.sim_keys is ignored).
 // peers: byte offsets from this rank's output buffers to the peers' (mz_set_peer_outputs).
+// A one-CTA kernel on `stream` that returns once flags[q] >= step for every q < world.
+int warp_peer_wait(WarpState& st, const int32_t* flags, int world, int step, cudaStream_t stream, int64_t* launches);
 int warp_launch(WarpState& st, const Tree& out, const SearchParams& p, const SimKeys* inline_keys, const float* obs,
                 const uint8_t* invalid, const float* noise, int32_t* action_out, float* weights_out,
                 float* root_value_out, const std::vector<int64_t>& peers, bool dump_tree, cudaStream_t stream,

@@ -714,7 +714,7 @@ static int search_device(mz_handle* h, const float* obs, const float* root_logit
   if (engine == MZ_ENGINE_AUTO || engine == MZ_ENGINE_FUSED)
     engine = warp_ok ? MZ_ENGINE_FUSED_WARP
                      : (treewarp_ok ? MZ_ENGINE_TREEWARP : (resident_ok ? MZ_ENGINE_RESIDENT : MZ_ENGINE_STEPWISE));
-  if (!h->peer_deltas.empty() && engine != MZ_ENGINE_FUSED_WARP)
+  if ((!h->peer_deltas.empty() || h->warpeng.flag != nullptr) && engine != MZ_ENGINE_FUSED_WARP)
     return fail("peer outputs (mz_set_peer_outputs) are written by the warp engine only; this configuration runs on "
                 "another engine — clear them and exchange the outputs with a collective");
   h->has_invalid = invalid != nullptr;
@@ -989,6 +989,25 @@ int mz_set_peer_outputs(mz_handle* h, int32_t n, const int64_t* byte_deltas) {
   if (h == nullptr || n < 0 || n > 7 || (n > 0 && byte_deltas == nullptr))
     return fail_arg("mz_set_peer_outputs: expected 0..7 byte offsets");
   h->peer_deltas.assign(byte_deltas, byte_deltas + n);
+  return 0;
+}
+
+int mz_set_peer_flags(mz_handle* h, int32_t* flags_dev, int32_t rank, int32_t step) {
+  using namespace mz;
+  if (h == nullptr || (flags_dev != nullptr && (rank < 0 || rank > 7))) return fail_arg("mz_set_peer_flags: bad argument");
+  h->warpeng.flag = flags_dev;
+  h->warpeng.flag_rank = rank;
+  h->warpeng.flag_step = step;
+  return 0;
+}
+
+int mz_peer_wait(mz_handle* h, const int32_t* flags_dev, int32_t world, int32_t step, void* stream) {
+  using namespace mz;
+  if (h == nullptr || flags_dev == nullptr || world < 1 || world > 8) return fail_arg("mz_peer_wait: bad argument");
+  if (!h->warpeng.available) return fail("mz_peer_wait: the warp engine is unavailable for this handle");
+  MZ_CUDA(cudaSetDevice(h->cfg.device));
+  if (warp_peer_wait(h->warpeng, flags_dev, world, step, (cudaStream_t)stream, &h->launches))
+    return fail("mz_peer_wait: launch failed");
   return 0;
 }
 

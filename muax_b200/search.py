@@ -137,6 +137,17 @@ class SearchEngine:
         arr = (ctypes.c_int64 * max(len(deltas), 1))(*deltas)
         _lib.check(self.lib.mz_set_peer_outputs(self._h, len(deltas), arr), "mz_set_peer_outputs")
 
+    def set_peer_flags(self, flags, rank=0, step=0):
+        """Completion flags of the peer-store exchange (include/mzsearch.h: mz_set_peer_flags): `flags` = int32 CUDA
+        tensor of W words inside this rank's symmetric gather buffer, or None to switch the signalling off."""
+        ptr = None if flags is None else flags.data_ptr()
+        _lib.check(self.lib.mz_set_peer_flags(self._h, ptr, int(rank), int(step)), "mz_set_peer_flags")
+
+    def peer_wait(self, flags, world, step):
+        """Enqueues, on the current stream, the wait for every rank's rows of act `step` (mz_peer_wait)."""
+        _lib.check(self.lib.mz_peer_wait(self._h, flags.data_ptr(), int(world), int(step),
+                                         _raw_stream(self.device.index)), "mz_peer_wait")
+
     # ------------------------------------------------------------------ arguments
     def make_args(self, rng_key, *, policy=_lib.POLICY_MUZERO, qtransform=None, num_simulations=5, temperature=1.0,
                   max_depth=None, dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25, pb_c_base=19652,

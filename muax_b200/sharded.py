@@ -42,13 +42,14 @@ class GatherHandle:
     (action, weights, value) views.  `launch` is separate from `act_async` so that a caller can place it (bench.py
     starts it together with the next act's search)."""
 
-    def __init__(self, owner, slot, local):
+    def __init__(self, owner, slot, local, peer_step=None):
         self._owner, self._slot, self.local = owner, slot, local
         self._work = None
         self._launched = False
+        self._peer_step = peer_step  # peer-store exchange: the act's number (the flags count acts)
 
     def launch(self):
-        if self._launched or self._owner.world == 1:
+        if self._launched or self._owner.world == 1 or self._peer_step is not None:
             self._launched = True
             return self
         o = self._owner
@@ -66,10 +67,16 @@ class GatherHandle:
         o = self._owner
         if o.world == 1:
             return self.local
-        self.launch()
-        self._work.wait()  # the current stream waits; the host does not
         n, A, W = o.count, o.A, o.world
-        r = o._async_recv[self._slot].view(W, n * (A + 2))
+        if self._peer_step is not None:
+            # the rows were stored here by the peers' own search kernels; wait for their completion flags
+            engine, bufs, flags = o._peer_async
+            engine.peer_wait(flags[self._slot], W, self._peer_step)
+            r = bufs[self._slot][:W * n * (A + 2)].view(W, n * (A + 2))
+        else:
+            self.launch()
+            self._work.wait()  # the current stream waits; the host does not
+            r = o._async_recv[self._slot].view(W, n * (A + 2))
         return (r[:, n * A + n:].view(torch.int32).reshape(W * n), r[:, :n * A].reshape(W * n, A),
                 r[:, n * A:n * A + n].reshape(W * n))
 
@@ -80,11 +87,13 @@ class ShardedSearch:
     search_fn(rng_key, obs_local, global_batch=..., batch_offset=..., **kw) -> (action, weights, value) tensors;
     with a `SearchEngine` pass `engine.search` (observations via `obs=`)."""
 
-    def __init__(self, search_fn, global_batch, num_actions, group=None, writes_into_out=False, peer_stores=False):
+    def __init__(self, search_fn, global_batch, num_actions, group=None, writes_into_out=False, peer_stores=False,
+                 engine=None):
         """writes_into_out: `search_fn` accepts `out=(action, weights, value)` and writes its results there
         (SearchEngine.search does).  With even shards the three outputs are then views of ONE flat send buffer, so
         the step is: search kernels -> one all-gather -> three strided copies, no packing kernels."""
         self.search_fn = search_fn
+        self._engine = engine  # the SearchEngine behind search_fn (or a callable returning it) when search_fn is a wrapper
         self.writes_into_out = bool(writes_into_out)
         self._send = self._recv = None
         self.global_batch = int(global_batch)
@@ -104,6 +113,8 @@ class ShardedSearch:
         self.exchange = "none" if self.world == 1 else "nccl all-gather"
         self._peer = None
         self._step = 0
+        self.async_slots = 3  # act_async: a handle stays valid until async_slots - 1 further acts have been issued
+        self.peer_slots = 4   # ... with the peer-store exchange (see _setup_peer_async)
 
     def local_rows(self, global_tensor):
         return global_tensor[self.offset:self.offset + self.count]
@@ -133,8 +144,8 @@ class ShardedSearch:
 
     def act_async(self, rng_key, obs_local, **kw):
         """Search this rank's rows now; exchange later.  Returns a GatherHandle: `.local` = this rank's
-        (action, weights, value), `.wait()` = everybody's.  Two send / receive buffer pairs alternate, so a handle stays
-        valid until the act after the next one is issued.  Needs even shards and a `search_fn` that writes into `out`."""
+        (action, weights, value), `.wait()` = everybody's.  `async_slots` (3) send / receive buffer pairs rotate, so a
+        handle stays valid until two further acts have been issued.  Needs even shards and a `search_fn` that writes into `out`."""
         if obs_local.shape[0] != self.count:
             raise ValueError(f"rank {self.rank} owns {self.count} rows, got {obs_local.shape[0]}")
         if self.world > 1 and (not self.writes_into_out or self.global_batch % self.world):
@@ -142,13 +153,16 @@ class ShardedSearch:
         n, A, W = self.count, self.A, self.world
         row = n * (A + 2)
         dev = obs_local.device
+        if W > 1 and self.peer_stores is not False and dev.type == "cuda":
+            if getattr(self, "_peer_async", None) is not None or self._setup_peer_async(dev, row):
+                return self._act_async_peer(rng_key, obs_local, row, **kw)
         if getattr(self, "_async_send", None) is None or self._async_send[0].device != dev:
-            self._async_send = [torch.empty(row, dtype=torch.float32, device=dev) for _ in range(2)]
-            self._async_recv = [torch.empty(W * row, dtype=torch.float32, device=dev) for _ in range(2)]
-            self._async_ready = [torch.cuda.Event() if dev.type == "cuda" else None for _ in range(2)]
+            self._async_send = [torch.empty(row, dtype=torch.float32, device=dev) for _ in range(self.async_slots)]
+            self._async_recv = [torch.empty(W * row, dtype=torch.float32, device=dev) for _ in range(self.async_slots)]
+            self._async_ready = [torch.cuda.Event() if dev.type == "cuda" else None for _ in range(self.async_slots)]
             self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
             self.exchange = "none" if W == 1 else "nccl all-gather on a side stream, overlapped with the next act"
-        slot = self._step & 1
+        slot = self._step % self.async_slots
         self._step += 1
         send = self._async_send[slot]
         out = (send[n * A + n:].view(torch.int32), send[:n * A].view(n, A), send[n * A:n * A + n])
@@ -234,6 +248,72 @@ class ShardedSearch:
             self.exchange = f"nccl all-gather (peer stores unavailable: {type(e).__name__})"
             self.peer_stores = False
             return False
+
+    def _resolve_engine(self):
+        e = self._engine() if callable(self._engine) else self._engine
+        return e if e is not None else getattr(self.search_fn, "__self__", None)
+
+    def _setup_peer_async(self, dev, row):
+        """The overlapped exchange without NCCL and without a barrier kernel: `peer_slots` symmetric gather buffers of
+        W rows + W completion flags each.  The search kernel stores its rows into every rank's buffer (NVLink peer
+        stores) and its last CTA sets this rank's flag everywhere; a consumer waits for W flags (mz_peer_wait).
+        Four slots: when rank A issues act s + 4 into slot s % 4 it has waited for act s + 2 of every peer, whose
+        stream-ordered consumption of act s (after its own wait, before its act s + 2) is therefore over."""
+        engine = self._resolve_engine()
+        if engine is None or not hasattr(engine, "set_peer_flags") or self.world > 8:
+            if self.peer_stores is True:
+                raise RuntimeError("peer stores need the SearchEngine behind search_fn (engine=)")
+            self.peer_stores = False
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            W = self.world
+            bufs, flags, deltas = [], [], []
+            for _ in range(self.peer_slots):
+                buf = symm.empty(W * row + W, dtype=torch.float32, device=dev)
+                hdl = symm.rendezvous(buf, group)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                buf.zero_()
+                bufs.append(buf)
+                flags.append(buf[W * row:].view(torch.int32))
+                deltas.append([ptrs[q] - ptrs[self.rank] for q in range(W) if q != self.rank])
+            torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.group)  # every rank's flags are zero before anybody's kernel may set them
+            self._peer_async = (engine, bufs, flags)
+            self._peer_async_deltas = deltas
+            self.exchange = "peer stores + completion flags from the search kernel (no NCCL, no barrier kernel)"
+            return True
+        except Exception as e:  # no P2P / symmetric memory on this system: keep the NCCL path, say so
+            if self.peer_stores is True:
+                raise
+            self.exchange = f"nccl all-gather on a side stream (peer stores unavailable: {type(e).__name__})"
+            self.peer_stores = False
+            return False
+
+    def _act_async_peer(self, rng_key, obs_local, row, **kw):
+        n, A = self.count, self.A
+        engine, bufs, flags = self._peer_async
+        slot = self._step % self.peer_slots
+        self._step += 1
+        step_no = self._step  # 1, 2, ...: the flags count acts
+        mine = bufs[slot][self.rank * row:(self.rank + 1) * row]
+        out = (mine[n * A + n:].view(torch.int32), mine[:n * A].view(n, A), mine[n * A:n * A + n])
+        engine.set_peer_outputs(self._peer_async_deltas[slot])
+        engine.set_peer_flags(flags[slot], self.rank, step_no)
+        try:
+            self.search_fn(rng_key, obs_local, global_batch=self.global_batch, batch_offset=self.offset, out=out, **kw)
+        except RuntimeError as e:
+            if self.peer_stores is True or "warp engine only" not in str(e):
+                raise
+            # this configuration runs on another engine: back to NCCL for good
+            self.peer_stores, self._peer_async = False, None
+            self._step -= 1
+            return self.act_async(rng_key, obs_local, **kw)
+        finally:
+            engine.set_peer_outputs([])
+            engine.set_peer_flags(None)
+        return GatherHandle(self, slot, out, peer_step=step_no)
 
     def _act_peer(self, rng_key, obs_local, row, **kw):
         n, A, W = self.count, self.A, self.world

@@ -61,6 +61,18 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.synchronize()
     res["async"] = [[t.cpu().numpy() for t in o] for o in outs]
     res["async_exchange"] = sh.exchange
+    # the same overlap with the kernel's own peer stores + completion flags (no NCCL, no barrier kernel); more acts
+    # than gather slots, so that the slots are reused
+    sh = ShardedSearch(eng.search, GB, A, writes_into_out=True, peer_stores=True)
+    handles, outs = [], []
+    for step in range(9):
+        handles.append(sh.act_async(np.array([7, step % 5], np.uint32), obs_local, num_simulations=NS))
+        if len(handles) == 2:
+            outs.append([t.clone() for t in handles.pop(0).wait()])
+    outs.append([t.clone() for t in handles.pop(0).wait()])
+    torch.cuda.synchronize()
+    res["async_peer"] = [[t.cpu().numpy() for t in o] for o in outs]
+    res["async_peer_exchange"] = sh.exchange
     # the end-to-end host path: NumPy rows in, everybody's results out (search + all-gather + one D2H)
     obs_local_np = obs[rank * n:(rank + 1) * n]
     res["host"] = [list(sh.act_host(np.array([7, step], np.uint32), obs_local_np, num_simulations=NS)) for step in range(5)]
@@ -74,8 +86,11 @@ def _worker(rank, world, port, out_dir):
         ok = all(np.array_equal(x, y) and np.array_equal(x, z) and np.array_equal(x, u) and np.array_equal(x, h)
                  for p, q, r, s, hh in zip(res["peer"], res["nccl"], ref, res["async"], res["host"])
                  for x, y, z, u, h in zip(p, q, r, s, hh))
+        ok = ok and len(res["async_peer"]) == 9 and all(
+            np.array_equal(x, y) for i, got in enumerate(res["async_peer"]) for x, y in zip(got, ref[i % 5]))
         with open(os.path.join(out_dir, "result.txt"), "w") as f:
-            f.write(f"{int(ok)}|{res['peer_exchange']}|{res['nccl_exchange']}|{res['async_exchange']}")
+            f.write(f"{int(ok)}|{res['peer_exchange']}|{res['nccl_exchange']}|{res['async_exchange']}|"
+                    f"{res['async_peer_exchange']}")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -87,8 +102,9 @@ def test_peer_stores_equal_nccl_all_gather_and_the_single_gpu_search(tmp_path):
     import torch.multiprocessing as mp
     world = 8 if torch.cuda.device_count() >= 8 else (4 if torch.cuda.device_count() >= 4 else 2)
     mp.spawn(_worker, args=(world, 29533, str(tmp_path)), nprocs=world, join=True)
-    ok, peer_exchange, nccl_exchange, async_exchange = open(tmp_path / "result.txt").read().split("|")
+    ok, peer_exchange, nccl_exchange, async_exchange, async_peer = open(tmp_path / "result.txt").read().split("|")
     assert peer_exchange.startswith("peer stores"), peer_exchange
     assert nccl_exchange.startswith("nccl"), nccl_exchange
     assert "side stream" in async_exchange, async_exchange
+    assert "completion flags" in async_peer, async_peer
     assert ok == "1"

@@ -15,11 +15,18 @@ done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_headline.csv python bench.py --steps 2 --warmup 3 > $O/l1.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_lunar.csv python bench.py --steps 2 --warmup 3 --workload lunarlander_mlp_e64_b4096_sim200 > $O/l2.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_atari_bf16.csv python bench.py --steps 2 --warmup 3 --workload atari_mlp_e256_b1024_sim50 --precision bf16 > $O/l3.log 2>&1
-# full captures of the top kernels
-ncu --set full --clock-control none --import-source on -k regex:warp_search -c 1 -s 3 -o $O/warp_full -f python bench.py --steps 2 --warmup 3 > $O/n1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:treewarp_search_kernel -c 1 -s 3 -o $O/treewarp_lunar_full -f python bench.py --steps 1 --warmup 3 --workload lunarlander_mlp_e64_b4096_sim200 > $O/n2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:recurrent_tc_kernel -c 1 -s 80 -o $O/recurrent_tc_atari_full -f python bench.py --steps 2 --warmup 3 --workload atari_mlp_e256_b1024_sim50 --precision bf16 > $O/n3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tw_backup_select_kernel -c 1 -s 80 -o $O/backup_select_atari_full -f python bench.py --steps 2 --warmup 3 --workload atari_mlp_e256_b1024_sim50 --precision bf16 > $O/n4.log 2>&1
+# full captures of the top kernels; summarised on the box (the .ncu-rep files together exceed what gpurun brings back)
+cap() {  # cap <name> <kernel regex> <mangled-name substring for the line attribution> <skip> <top> <bench args...>
+  local name=$1 rx=$2 sub=$3 skip=$4 top=$5; shift 5
+  ncu --set full --clock-control none --import-source on -k regex:$rx -c 1 -s $skip -o $O/$name -f python bench.py "$@" > $O/$name.log 2>&1
+  python tools/ncu_summary.py $O/$name.ncu-rep > $O/${name}_summary.txt 2>&1
+  python tools/ncu_lines.py $O/$name.ncu-rep $sub $top > $O/${name}_lines.txt 2>&1
+  rm -f $O/$name.ncu-rep
+}
+cap warp_full warp_search warp_search_kernelILi2ELi8ELi16ELi10ELi16 3 32 --steps 2 --warmup 3
+cap treewarp_lunar_full treewarp_search_kernel treewarp_search_kernel 3 30 --steps 1 --warmup 3 --workload lunarlander_mlp_e64_b4096_sim200
+cap recurrent_tc_atari_full recurrent_tc_kernel recurrent_tc_kernel 80 30 --steps 2 --warmup 3 --workload atari_mlp_e256_b1024_sim50 --precision bf16
+cap backup_select_atari_full tw_backup_select_kernel tw_backup_select_kernel 80 25 --steps 2 --warmup 3 --workload atari_mlp_e256_b1024_sim50 --precision bf16
 # tcgen05 kernel timeline (instrumented build)
 MZ_LIB_PATH=$PWD/muax_b200/libmzsearch_clk.so timeout 300 python bench.py --workload atari_mlp_e256_b1024_sim50 --steps 1 --warmup 3 --precision bf16 2>&1 | grep "tc clk" | tail -2 > $O/tc_clk_search_atari.txt
 MZ_LIB_PATH=$PWD/muax_b200/libmzsearch_clk.so timeout 300 python tools/bench_recurrent.py 2>&1 | grep -E "tc clk|us_per_call" > $O/tc_clk_micro.txt

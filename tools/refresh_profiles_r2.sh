@@ -1,13 +1,10 @@
 # Copies the artefacts of tools/final_measure_r2.sh (gpurun_out/final2/) into profiles/ as round-2 evidence.
 O=gpurun_out/final2
-python tools/ncu_summary.py $O/warp_full.ncu-rep > profiles/r02_warp_summary.txt
-python tools/ncu_lines.py $O/warp_full.ncu-rep warp_search_kernelILi2ELi8ELi16ELi10ELi16 30 > profiles/r02_warp_lines.txt 2>&1
-python tools/ncu_summary.py $O/treewarp_lunar_full.ncu-rep > profiles/r02_treewarp_lunar_summary.txt
-python tools/ncu_lines.py $O/treewarp_lunar_full.ncu-rep treewarp_search_kernel 30 > profiles/r02_treewarp_lunar_lines.txt 2>&1
-python tools/ncu_summary.py $O/recurrent_tc_atari_full.ncu-rep > profiles/r02_recurrent_tc_atari_summary.txt
-python tools/ncu_lines.py $O/recurrent_tc_atari_full.ncu-rep recurrent_tc_kernel 30 > profiles/r02_recurrent_tc_atari_lines.txt 2>&1
-python tools/ncu_summary.py $O/backup_select_atari_full.ncu-rep > profiles/r02_backup_select_atari_summary.txt
-python tools/ncu_lines.py $O/backup_select_atari_full.ncu-rep tw_backup_select_kernel 25 > profiles/r02_backup_select_atari_lines.txt 2>&1
+for pair in warp_full:warp treewarp_lunar_full:treewarp_lunar recurrent_tc_atari_full:recurrent_tc_atari backup_select_atari_full:backup_select_atari; do
+  src=${pair%%:*}; dst=${pair##*:}
+  cp $O/${src}_summary.txt profiles/r02_${dst}_summary.txt
+  cp $O/${src}_lines.txt profiles/r02_${dst}_lines.txt
+done
 python tools/launch_summary.py $O/launches_headline.csv "bench.py --steps 2 --warmup 3 (headline workload, engine auto = warp)" > profiles/r02_launches_headline_summary.txt
 python tools/launch_summary.py $O/launches_lunar.csv "bench.py --workload lunarlander_mlp_e64_b4096_sim200 (engine auto = tree-warp)" > profiles/r02_launches_lunar_treewarp_summary.txt
 python tools/launch_summary.py $O/launches_atari_bf16.csv "bench.py --workload atari_mlp_e256_b1024_sim50 --precision bf16 (throughput mode)" > profiles/r02_launches_atari_bf16_summary.txt
