@@ -22,6 +22,8 @@ struct TreeWarpState {
   int noise_levels = 32;  // MZ_TREEWARP_K: tie-break noise levels produced ahead of the search
   int prefetch = 0;       // MZ_TREEWARP_PREFETCH: prefetch the children's records while a level is scored
   void* batched = nullptr;  // state of the per-simulation kernels (throughput mode)
+  void* scores = nullptr;   // MZ_TW_CACHED builds: [B][NS + 1][A] float2 selection-score cache of the fused kernel
+  size_t scores_bytes = 0;
 };
 
 int treewarp_init(TreeWarpState& st, const Net& net, int device, std::string* err);
