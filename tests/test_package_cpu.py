@@ -170,3 +170,21 @@ def test_checkpoint_interop_and_load_without_init(tmp_path):
     third = muax_b200.MuZero(net, policy="muzero", support_size=10)
     third.params = tilde                                             # reference-spelled params straight in
     assert np.array_equal(third._spec.pack(third.params)[0], blob_a)
+
+
+def test_sass_size_map_tool_reads_the_built_library(lib):
+    """tools/sass_size_map.py (the map behind DESIGN.md §3.1b's instruction-fetch finding) parses the library built
+    here: a small kernel is enough — every instruction lands on a source line of its own translation unit."""
+    import shutil
+    import subprocess
+    import sys
+    if not (shutil.which("cuobjdump") and shutil.which("nvdisasm")):
+        pytest.skip("CUDA binary utilities not on PATH")
+    from muax_b200 import _lib
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_size_map.py"), "recurrent_tc_bias_kernel",
+                          _lib.LIB_PATH, "5"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-400:]
+    head = out.stdout.splitlines()[0]
+    m = re.search(r"recurrent_tc_bias_kernel\S*: (\d+) bytes of SASS \((\d+) instructions\)", head)
+    assert m and int(m.group(1)) == 16 * int(m.group(2)) > 0
+    assert "mz_recurrent_tc.cu:" in out.stdout
